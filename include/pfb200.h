@@ -1,0 +1,170 @@
+/*
+ * pfb200.h -- C ABI of the B200-native (sm_100a) sequential Monte Carlo state estimator.
+ *
+ * Drop-in boundary for the hot path of compops/qnmh-sysid2018: the bootstrap particle filter and
+ * fixed-lag particle smoother of python/state/particle_methods.  The entry points below are what
+ * the reference's native boundary for this path binds (citations are relative to the reference
+ * repository root):
+ *
+ *   reference interface                                               replaced by
+ *   ----------------------------------------------------------------  ---------------------------
+ *   bpf_lgss(obs, mu, phi, sigmav, sigmae) -> (filt, ll, traj)         pfb200_run(do_smoother=0)
+ *     python/state/particle_methods/cython_lgss_helper.pyx:35,140
+ *   flps_lgss(obs, mu, phi, sigmav, sigmae)                            pfb200_run(do_smoother=1)
+ *     -> (filt, smo, ll, gradient[4][NoObs], traj)
+ *     python/state/particle_methods/cython_lgss_helper.pyx:144,335
+ *   bpf_sv / flps_sv (obs, mu, phi, sigmav)                            pfb200_run(model=PFB200_MODEL_SV)
+ *     python/state/particle_methods/cython_sv_helper.pyx:35,144
+ *   bpf_sv / flps_sv (obs, mu, phi, sigmav, rho)                       pfb200_run(model=PFB200_MODEL_SVL)
+ *     python/state/particle_methods/cython_sv_leverage_helper.pyx:35,146
+ *   ParticleMethods.filter / .smoother (NumPy twin, run-time N/T/L)    same calls; semantics follow
+ *     python/state/particle_methods/standard.py:42,121                 the NumPy path
+ *   systematic / stratified resampling                                 `resampling` argument
+ *     python/state/particle_methods/resampling.pyx:44,65
+ *
+ * Conventions: every pointer is a HOST pointer owned by the caller unless stated otherwise; arrays
+ * are C-contiguous doubles in time-major order; the library owns all device memory inside the
+ * handle.  No exceptions cross the boundary: every call returns 0 on success or a negative
+ * PFB200_E* code, and pfb200_last_error() returns a human readable message for the calling
+ * thread's most recent failure.  A handle is bound to one CUDA device and one stream and is not
+ * thread-safe; different handles may be used from different threads.  There is no CPU fallback:
+ * without a usable CUDA device pfb200_create fails with PFB200_ENODEVICE.
+ */
+#ifndef PFB200_H_
+#define PFB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB200_ABI_VERSION 1
+
+/* model_id: which per-particle model arithmetic runs on the device */
+#define PFB200_MODEL_LGSS 0 /* models/linear_gaussian_model.py:            theta = mu, phi, sigma_v, sigma_e */
+#define PFB200_MODEL_SV 1   /* models/stochastic_volatility_model.py:      theta = mu, phi, sigma_v          */
+#define PFB200_MODEL_SVL 2  /* models/stochastic_volatility_model_leverage.py: theta = mu, phi, sigma_v, rho */
+
+/* dtype: storage / per-particle arithmetic type (CDF, reductions and outputs are always fp64) */
+#define PFB200_F64 0
+#define PFB200_F32 1
+
+/* resampling (resampling.pyx) */
+#define PFB200_RESAMPLE_SYSTEMATIC 0
+#define PFB200_RESAMPLE_STRATIFIED 1
+
+/* flags (bit mask) */
+#define PFB200_FLAG_STORE_HISTORY 1u    /* keep all T+1 generations (particles, log-weights, ancestors) */
+#define PFB200_FLAG_OBS_PER_FILTER 2u   /* obs is [B][T+1] instead of one shared [T+1] series */
+#define PFB200_FLAG_SVL_OBS_MODEL 4u    /* SV-leverage: propagate with obs[t-1] (model-consistent, Cython twin)
+                                           instead of obs[t] (NumPy twin) */
+#define PFB200_FLAG_INJECT_PER_FILTER 8u /* injected randomness is given per filter ([B][...]) */
+
+/* error codes */
+#define PFB200_OK 0
+#define PFB200_EINVAL -1
+#define PFB200_ENODEVICE -2
+#define PFB200_ECUDA -3
+#define PFB200_ENOMEM -4
+#define PFB200_ESTATE -5
+#define PFB200_ETIMEOUT -6
+
+typedef struct pfb200_handle pfb200_handle;
+
+/* Number of parameters P of a model (4, 3, 4); negative on an unknown model. */
+int pfb200_model_no_params(int model_id);
+int pfb200_abi_version(void);
+const char* pfb200_last_error(void);
+
+/* Creates an estimator bound to CUDA device `device` (-1: current device). */
+int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out);
+int pfb200_destroy(pfb200_handle* h);
+
+/* Uses `cuda_stream` (a cudaStream_t, e.g. torch's current stream) for all work; NULL restores
+ * the handle's own stream. */
+int pfb200_set_stream(pfb200_handle* h, void* cuda_stream);
+
+/* Tuning knobs (defaults are chosen from the problem size):
+ *   "ctas_per_filter"  G: CTAs cooperating on one filter (0 = automatic)
+ *   "max_groups"       upper bound on concurrently resident filter groups (0 = automatic)
+ *   "spin_limit"       abort a launch whose inter-CTA exchange spins longer than this many polls */
+int pfb200_set_option(pfb200_handle* h, const char* name, long long value);
+int pfb200_get_info(pfb200_handle* h, const char* name, long long* value);
+
+/*
+ * Describes the next evaluation(s) and uploads the inputs to the device (H2D on the handle's
+ * stream).  B = n_filters independent evaluations are run side by side (MH proposals, Monte Carlo
+ * replicates).
+ *
+ *   obs        [T+1] (or [B][T+1] with PFB200_FLAG_OBS_PER_FILTER); obs[0] is the dummy initial row
+ *   theta      [B][P] model parameters in the reference's order (get_all_params())
+ *   seed, eval_ids[B] (NULL -> 0..B-1): Philox4x32-10 stream = (seed, eval_id); a draw depends only
+ *              on (seed, eval_id, time step, particle index), never on the launch geometry
+ *   inj_z0 [N], inj_u [T+1] ([T+1][N] for stratified), inj_z [T+1][N], inj_u_final [1]:
+ *              injected randomness replacing Philox (all four or none; NULL = Philox); with
+ *              PFB200_FLAG_INJECT_PER_FILTER each carries a leading [B] dimension.  Row t of
+ *              inj_u / inj_z is consumed at time step t (row 0 is unused).
+ */
+int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_obs, int fixed_lag,
+                     int do_smoother, int generate_initial_state, double initial_state,
+                     int resampling, unsigned flags, const double* obs, const double* theta,
+                     uint64_t seed, const uint64_t* eval_ids, const double* inj_z0,
+                     const double* inj_u, const double* inj_z, const double* inj_u_final);
+
+/* Re-uploads only theta / eval_ids for the configured problem (what an MH iteration changes). */
+int pfb200_update_params(pfb200_handle* h, const double* theta, uint64_t seed,
+                         const uint64_t* eval_ids);
+
+/* Enqueues the filter (+ smoother) kernels on the handle's stream.  Asynchronous. */
+int pfb200_execute(pfb200_handle* h);
+
+/* Waits for the stream; reports a device-side abort (exchange time-out) as PFB200_ETIMEOUT. */
+int pfb200_synchronize(pfb200_handle* h);
+
+/* Device time of the most recent pfb200_execute in ms (CUDA events on the handle's stream). */
+int pfb200_last_execute_ms(pfb200_handle* h, float* ms);
+
+/*
+ * Copies results to host memory (D2H on the stream, then waits).  Any pointer may be NULL.
+ *   log_like   [B]            sum_t ( m_t + log S_t - log N )           standard.py:96-98,110
+ *   filt       [B][T+1]       filtered means (entry 0 is 0)             standard.py:101
+ *   smo        [B][T+1]       fixed-lag smoothed means                  standard.py:140-157
+ *   grad_terms [B][P][T+1]    G[p][i] = sum_n w_lag[n] d_p log p(x_{i+1}, y_i | x_i)   standard.py:161-169
+ *   traj_index [B]            row index of the trajectory draw          standard.py:104-105
+ *   traj       [B][T+1]       particles[traj_index, :]; needs PFB200_FLAG_STORE_HISTORY (else NaN)
+ */
+int pfb200_fetch(pfb200_handle* h, double* log_like, double* filt, double* smo, double* grad_terms,
+                 int32_t* traj_index, double* traj);
+
+/* Per-step diagnostics: log-likelihood terms [B][T+1], max log-weight m_t and sum S_t. */
+int pfb200_fetch_steps(pfb200_handle* h, double* ll_terms, double* max_logw, double* sum_w);
+
+/* Full history (PFB200_FLAG_STORE_HISTORY only), time-major: particles/log_weights [B][T+1][N]
+ * (converted to double), ancestors [B][T+1][N] int32. */
+int pfb200_fetch_history(pfb200_handle* h, double* particles, double* log_weights,
+                         int32_t* ancestors);
+
+/* Convenience: configure + execute + fetch in one call with host buffers (the end-to-end path
+ * the reference's flps_* / bpf_* calls map to). */
+int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, int fixed_lag,
+               int do_smoother, int generate_initial_state, double initial_state, int resampling,
+               unsigned flags, const double* obs, const double* theta, uint64_t seed,
+               const uint64_t* eval_ids, const double* inj_z0, const double* inj_u,
+               const double* inj_z, const double* inj_u_final, double* log_like, double* filt,
+               double* smo, double* grad_terms, int32_t* traj_index, double* traj);
+
+/* Writes the standard normals the Philox path uses at time step t (0 = initial state) for
+ * particles [0, N) of evaluation eval_id into host array z[N] (for replaying a Philox run through
+ * a CPU checker). */
+int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int n,
+                          double* z);
+/* The resampling uniform(s) the Philox path uses at time step t (count = 1 systematic, N stratified;
+ * t = -1: the trajectory-draw uniform). */
+int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int count,
+                           double* u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB200_H_ */

@@ -1,0 +1,246 @@
+// Device-side building blocks of the B200 particle filter / fixed-lag smoother:
+// Philox4x32-10 counter RNG, the per-particle model arithmetic of the three reference models,
+// inter-CTA exchange primitives and block-level scan / reduce helpers.
+//
+// Reference behaviour restated here (paths relative to the reference repository root):
+//   models/linear_gaussian_model.py:77-107,142-154,208-244          (LGSS callbacks)
+//   models/stochastic_volatility_model.py:74-104,137-150,200-230     (SV callbacks)
+//   models/stochastic_volatility_model_leverage.py:77-108,143-156,212-259 (SV with leverage)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pfb200 {
+
+constexpr int kMaxParams = 4;
+constexpr int kNumConsts = 16;
+constexpr int kModelLGSS = 0, kModelSV = 1, kModelSVL = 2;
+
+// Derived per-filter constants, computed on the host with the reference's own expressions
+// (so that e.g. sigma_v**(-2) has the bits Python gives it) -- see host_consts() in pfb200.cu.
+enum ConstIdx {
+  C_MU = 0, C_PHI, C_SIGV, C_SIGE_OR_RHO, C_SD0, C_LOGSIGE, C_Q, C_R, C_1MPHI, C_1MPHI2,
+  C_SVRHO, C_STDEV, C_RHOTERM, C_RHOINV_RHO, C_UNUSED0, C_UNUSED1
+};
+
+#define PFB_NORM_LOGC 0.91893853320467267  // log(sqrt(2 pi)), scipy _norm_pdf_logC
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter = (index, time step, eval_id lo, stream|eval_id hi),
+// key = seed.  A draw is a pure function of (seed, eval_id, stream, t, index).
+// ------------------------------------------------------------------------------------------
+enum PhiloxStream : unsigned { kStreamZ = 0u, kStreamU = 1u, kStreamUFinal = 2u };
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n1 = (uint32_t)p1;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  const uint32_t n3 = (uint32_t)p0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t eval_id, unsigned stream,
+                                                       uint32_t t, uint32_t index, uint32_t (&out)[4]) {
+  uint32_t c[4] = {index, t, (uint32_t)eval_id, (uint32_t)(eval_id >> 32) ^ (stream << 28)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// uniform in [0,1) with 53 random bits (numpy's uniform() is also [0,1))
+__host__ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
+  const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return (double)v * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t eval_id, unsigned stream,
+                                                 uint32_t t, uint32_t index) {
+  uint32_t r[4];
+  philox4x32_10(seed, eval_id, stream, t, index, r);
+  return u01_53(r[0], r[1]);
+}
+
+// Two standard normals for the particle pair (2*pair, 2*pair+1) at time step t (Box-Muller on
+// one Philox block, both branches used).
+template <typename Real>
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t eval_id, uint32_t t,
+                                                   uint32_t pair, Real& z_even, Real& z_odd);
+
+template <>
+__device__ __forceinline__ void philox_normal_pair<double>(uint64_t seed, uint64_t eval_id, uint32_t t,
+                                                           uint32_t pair, double& z_even, double& z_odd) {
+  uint32_t r[4];
+  philox4x32_10(seed, eval_id, kStreamZ, t, pair, r);
+  const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
+  const double u2 = u01_53(r[2], r[3]);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z_even = rad * c;
+  z_odd = rad * s;
+}
+
+template <>
+__device__ __forceinline__ void philox_normal_pair<float>(uint64_t seed, uint64_t eval_id, uint32_t t,
+                                                          uint32_t pair, float& z_even, float& z_odd) {
+  uint32_t r[4];
+  philox4x32_10(seed, eval_id, kStreamZ, t, pair, r);
+  const float u1 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+  const float u2 = (float)(r[2] >> 8) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  z_even = rad * c;
+  z_odd = rad * s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-particle model arithmetic.  The fp64 propagate / weight paths pin the reference's operation
+// order with round-to-nearest intrinsics (never contracted to FMA), so that with injected noise a
+// particle has the same bits as in the NumPy reference.  fp32 uses fast intrinsics.
+// ------------------------------------------------------------------------------------------
+template <int MODEL, typename Real>
+struct ModelOps;
+
+template <int MODEL>
+struct ModelOps<MODEL, double> {
+  // generate_initial_state: mu + (sigma_v / sqrt(1 - phi**2)) * z
+  static __device__ __forceinline__ double init(const double* c, double z) {
+    return __dadd_rn(c[C_MU], __dmul_rn(c[C_SD0], z));
+  }
+  // generate_state; y is the observation the model reads for the leverage term
+  static __device__ __forceinline__ double propagate(const double* c, double x, double z, double y) {
+    double mean = __dadd_rn(c[C_MU], __dmul_rn(c[C_PHI], __dsub_rn(x, c[C_MU])));
+    if (MODEL == kModelSVL) {
+      const double lev = __dmul_rn(__dmul_rn(c[C_SVRHO], exp(__dmul_rn(-0.5, x))), y);
+      mean = __dadd_rn(mean, lev);
+      return __dadd_rn(mean, __dmul_rn(c[C_STDEV], z));
+    }
+    return __dadd_rn(mean, __dmul_rn(c[C_SIGV], z));
+  }
+  // evaluate_obs = scipy.stats.norm.logpdf
+  static __device__ __forceinline__ double logweight(const double* c, double x, double y) {
+    if (MODEL == kModelLGSS) {
+      const double zz = __ddiv_rn(__dsub_rn(y, x), c[C_SIGE_OR_RHO]);
+      return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), c[C_LOGSIGE]);
+    } else {
+      const double vol = exp(__dmul_rn(0.5, x));
+      const double zz = __ddiv_rn(y, vol);
+      return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), log(vol));
+    }
+  }
+  // log_joint_gradient(next_state, cur_state, time_index); out[p] in parameter order
+  static __device__ __forceinline__ void gradient(const double* c, double xn, double xc, double y,
+                                                  double (&out)[kMaxParams]) {
+    double q = xn - c[C_MU];
+    q = q - c[C_PHI] * (xc - c[C_MU]);
+    double e = 0.0;
+    if (MODEL == kModelSVL) {
+      e = exp(-0.5 * xc);
+      q = q - c[C_SVRHO] * e * y;
+    }
+    const double Q = c[C_Q];
+    out[0] = Q * q * c[C_1MPHI];
+    out[1] = Q * q * (xc - c[C_MU]) * c[C_1MPHI2];
+    out[2] = Q * (q * q) - 1.0;
+    if (MODEL == kModelLGSS) {
+      const double oq = y - xc;
+      out[3] = c[C_R] * (oq * oq) - 1.0;
+    } else if (MODEL == kModelSVL) {
+      const double rho = c[C_SIGE_OR_RHO], sv = c[C_SIGV];
+      out[2] = out[2] + q * rho * sv * y * e * Q * sv;
+      double gr = c[C_RHOINV_RHO];
+      gr = gr + q * sv * y * e * Q;
+      gr = gr - (-rho * (q * q) * Q / c[C_RHOTERM]);
+      out[3] = gr * c[C_RHOTERM];
+    } else {
+      out[3] = 0.0;
+    }
+  }
+};
+
+template <int MODEL>
+struct ModelOps<MODEL, float> {
+  static __device__ __forceinline__ float init(const double* c, float z) {
+    return (float)c[C_MU] + (float)c[C_SD0] * z;
+  }
+  static __device__ __forceinline__ float propagate(const double* c, float x, float z, double y) {
+    const float mu = (float)c[C_MU];
+    float mean = mu + (float)c[C_PHI] * (x - mu);
+    if (MODEL == kModelSVL) {
+      mean += (float)c[C_SVRHO] * __expf(-0.5f * x) * (float)y;
+      return mean + (float)c[C_STDEV] * z;
+    }
+    return mean + (float)c[C_SIGV] * z;
+  }
+  static __device__ __forceinline__ float logweight(const double* c, float x, double y) {
+    if (MODEL == kModelLGSS) {
+      const float zz = ((float)y - x) * (float)(1.0 / c[C_SIGE_OR_RHO]);
+      return -0.5f * zz * zz - (float)PFB_NORM_LOGC - (float)c[C_LOGSIGE];
+    } else {
+      // -0.5 y^2 exp(-x) - logC - x/2   (log(exp(x/2)) folded analytically in fp32)
+      const float yy = (float)y;
+      return -0.5f * yy * yy * __expf(-x) - (float)PFB_NORM_LOGC - 0.5f * x;
+    }
+  }
+  static __device__ __forceinline__ void gradient(const double* c, float xn, float xc, double y,
+                                                  double (&out)[kMaxParams]) {
+    // score terms are accumulated in fp64 from the fp32 states
+    ModelOps<MODEL, double>::gradient(c, (double)xn, (double)xc, y, out);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Memory-ordering helpers for the inter-CTA exchange (gpu scope).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_i32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// L2-coherent loads for data produced by other CTAs of the same launch (never served from a
+// stale L1 line; the rings reuse addresses every few steps).
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T* p) {
+  return __ldcg(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp / block helpers (fixed reduction trees: results do not depend on scheduling)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+}  // namespace pfb200

@@ -1,0 +1,580 @@
+// C-ABI host side of libpfb200.so (see include/pfb200.h): device workspace management, launch
+// geometry, H2D/D2H staging.  No PyTorch types; plain CUDA runtime.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfb200.h"
+#include "pf_kernels.cuh"
+
+using namespace pfb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess)                                                             \
+      return fail(err__ == cudaErrorMemoryAllocation ? PFB200_ENOMEM : PFB200_ECUDA,      \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    if (bytes == 0) return cudaSuccess;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      want = bytes;
+      e = cudaMalloc(&ptr, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+constexpr int kBlock = 512;
+constexpr int kItems = 7;
+constexpr int kChunk = kBlock * kItems;
+
+typedef void (*KernelFn)(const DeviceProblem);
+
+template <typename Real>
+KernelFn kernel_for_model(int model) {
+  switch (model) {
+    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems>;
+    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems>;
+    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems>;
+  }
+  return nullptr;
+}
+
+// Derived constants with the reference's own expressions (Python float arithmetic == C double):
+//   linear_gaussian_model.py:87-90,223-237; stochastic_volatility_model_leverage.py:103-108,227-252
+void host_consts(int model, const double* th, double* c) {
+  for (int i = 0; i < kNumConsts; ++i) c[i] = 0.0;
+  const double mu = th[0], phi = th[1], sv = th[2];
+  c[C_MU] = mu;
+  c[C_PHI] = phi;
+  c[C_SIGV] = sv;
+  c[C_SD0] = sv / std::sqrt(1.0 - std::pow(phi, 2.0));
+  c[C_Q] = std::pow(sv, -2.0);
+  c[C_1MPHI] = 1.0 - phi;
+  c[C_1MPHI2] = 1.0 - std::pow(phi, 2.0);
+  if (model == kModelLGSS) {
+    const double se = th[3];
+    c[C_SIGE_OR_RHO] = se;
+    c[C_LOGSIGE] = std::log(se);
+    c[C_R] = std::pow(se, -2.0);
+  } else if (model == kModelSVL) {
+    const double rho = th[3];
+    const double rho_term = 1.0 - std::pow(rho, 2.0);
+    c[C_SIGE_OR_RHO] = rho;
+    c[C_SVRHO] = sv * rho;
+    c[C_STDEV] = std::sqrt(1.0 - std::pow(rho, 2.0)) * sv;
+    c[C_RHOTERM] = rho_term;
+    c[C_Q] = std::pow(sv, -2.0) * std::pow(rho_term, -1.0);
+    c[C_RHOINV_RHO] = std::pow(rho_term, -1.0) * rho;
+  }
+}
+
+}  // namespace
+
+struct pfb200_handle {
+  int device = 0;
+  int model = 0;
+  int dtype = 0;
+  int P = 0;
+  int num_sms = 0;
+  int blocks_per_sm = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  KernelFn kernel = nullptr;
+  // options
+  long long opt_ctas_per_filter = 0;
+  long long opt_max_groups = 0;
+  long long opt_spin_limit = 20000000LL;
+  // configured problem
+  bool configured = false;
+  bool executed = false;
+  DeviceProblem prob{};
+  unsigned flags = 0;
+  size_t smem_bytes = 0;
+  bool cooperative = false;
+  int n_ws = 0;
+  // device buffers
+  DevBuf obs, consts, evals, inj_z0, inj_u, inj_z, inj_uf;
+  DevBuf x_ring, logw, anc, xval, xflag, abortf;
+  DevBuf stat_m, stat_S, filt_part, smo_part, traj_k, traj_idx;
+  DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch;
+  std::vector<double> h_consts;
+  std::vector<unsigned long long> h_evals;
+};
+
+extern "C" {
+
+int pfb200_abi_version(void) { return PFB200_ABI_VERSION; }
+
+const char* pfb200_last_error(void) { return g_last_error.c_str(); }
+
+int pfb200_model_no_params(int model_id) {
+  switch (model_id) {
+    case PFB200_MODEL_LGSS: return 4;
+    case PFB200_MODEL_SV: return 3;
+    case PFB200_MODEL_SVL: return 4;
+  }
+  return PFB200_EINVAL;
+}
+
+int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
+  if (!out) return fail(PFB200_EINVAL, "pfb200_create: out is NULL");
+  *out = nullptr;
+  const int P = pfb200_model_no_params(model_id);
+  if (P < 0) return fail(PFB200_EINVAL, "pfb200_create: unknown model_id %d", model_id);
+  if (dtype != PFB200_F64 && dtype != PFB200_F32) return fail(PFB200_EINVAL, "pfb200_create: unknown dtype %d", dtype);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return fail(PFB200_ENODEVICE, "pfb200_create: no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= count) return fail(PFB200_EINVAL, "pfb200_create: device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  pfb200_handle* h = new pfb200_handle();
+  h->device = device;
+  h->model = model_id;
+  h->dtype = dtype;
+  h->P = P;
+  h->kernel = dtype == PFB200_F64 ? kernel_for_model<double>(model_id) : kernel_for_model<float>(model_id);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  *out = h;
+  return PFB200_OK;
+}
+
+int pfb200_destroy(pfb200_handle* h) {
+  if (!h) return PFB200_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->obs, &h->consts, &h->evals, &h->inj_z0, &h->inj_u, &h->inj_z, &h->inj_uf, &h->x_ring,
+                    &h->logw, &h->anc, &h->xval, &h->xflag, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
+                    &h->smo_part, &h->traj_k, &h->traj_idx, &h->ll_terms, &h->log_like, &h->filt, &h->smo,
+                    &h->grad, &h->traj, &h->scratch};
+  for (DevBuf* b : bufs) b->release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return PFB200_OK;
+}
+
+int pfb200_set_stream(pfb200_handle* h, void* cuda_stream) {
+  if (!h) return fail(PFB200_EINVAL, "pfb200_set_stream: NULL handle");
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return PFB200_OK;
+}
+
+int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
+  if (!h || !name) return fail(PFB200_EINVAL, "pfb200_set_option: NULL argument");
+  if (!strcmp(name, "ctas_per_filter")) h->opt_ctas_per_filter = value;
+  else if (!strcmp(name, "max_groups")) h->opt_max_groups = value;
+  else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
+  else return fail(PFB200_EINVAL, "pfb200_set_option: unknown option '%s'", name);
+  h->configured = false;
+  return PFB200_OK;
+}
+
+int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
+  if (!h || !name || !value) return fail(PFB200_EINVAL, "pfb200_get_info: NULL argument");
+  if (!strcmp(name, "num_sms")) *value = h->num_sms;
+  else if (!strcmp(name, "ctas_per_filter")) *value = h->prob.G;
+  else if (!strcmp(name, "n_groups")) *value = h->prob.n_groups;
+  else if (!strcmp(name, "per_cta")) *value = h->prob.per_cta;
+  else if (!strcmp(name, "block_threads")) *value = kBlock;
+  else if (!strcmp(name, "chunk")) *value = kChunk;
+  else if (!strcmp(name, "blocks_per_sm")) *value = h->blocks_per_sm;
+  else if (!strcmp(name, "cooperative")) *value = h->cooperative ? 1 : 0;
+  else if (!strcmp(name, "smem_bytes")) *value = (long long)h->smem_bytes;
+  else if (!strcmp(name, "kernel_launches_per_execute")) *value = 2 + ((h->flags & PFB200_FLAG_STORE_HISTORY) ? 1 : 0);
+  else if (!strcmp(name, "workspace_bytes")) {
+    *value = (long long)(h->x_ring.cap + h->logw.cap + h->anc.cap + h->filt_part.cap + h->smo_part.cap);
+  } else return fail(PFB200_EINVAL, "pfb200_get_info: unknown key '%s'", name);
+  return PFB200_OK;
+}
+
+static int upload_params(pfb200_handle* h, const double* theta, uint64_t seed, const uint64_t* eval_ids) {
+  const int B = h->prob.B;
+  h->h_consts.resize((size_t)B * kNumConsts);
+  h->h_evals.resize(B);
+  for (int b = 0; b < B; ++b) {
+    host_consts(h->model, theta + (size_t)b * h->P, h->h_consts.data() + (size_t)b * kNumConsts);
+    h->h_evals[b] = eval_ids ? eval_ids[b] : (unsigned long long)b;
+  }
+  h->prob.seed = seed;
+  CUDA_TRY(cudaMemcpyAsync(h->consts.ptr, h->h_consts.data(), h->h_consts.size() * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->evals.ptr, h->h_evals.data(), h->h_evals.size() * sizeof(unsigned long long),
+                           cudaMemcpyHostToDevice, h->stream));
+  // the staging vectors are pageable: the copies above have completed on return
+  return PFB200_OK;
+}
+
+int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_obs, int fixed_lag,
+                     int do_smoother, int generate_initial_state, double initial_state,
+                     int resampling, unsigned flags, const double* obs, const double* theta,
+                     uint64_t seed, const uint64_t* eval_ids, const double* inj_z0,
+                     const double* inj_u, const double* inj_z, const double* inj_u_final) {
+  if (!h) return fail(PFB200_EINVAL, "pfb200_configure: NULL handle");
+  h->configured = false;
+  h->executed = false;
+  const int B = n_filters, N = no_particles, T = no_obs, L = fixed_lag, P = h->P;
+  if (B < 1 || N < 1 || T < 1 || L < 0)
+    return fail(PFB200_EINVAL, "pfb200_configure: need n_filters>=1, no_particles>=1, no_obs>=1, fixed_lag>=0 (got %d,%d,%d,%d)", B, N, T, L);
+  if (N > (1 << 30)) return fail(PFB200_EINVAL, "pfb200_configure: no_particles %d exceeds 2^30", N);
+  if (do_smoother && L < 1)
+    return fail(PFB200_EINVAL, "pfb200_configure: the fixed-lag smoother needs fixed_lag >= 1 (the reference raises NameError at standard.py:161 for fixed_lag=0)");
+  if (resampling != PFB200_RESAMPLE_SYSTEMATIC && resampling != PFB200_RESAMPLE_STRATIFIED)
+    return fail(PFB200_EINVAL, "pfb200_configure: unsupported resampling method %d", resampling);
+  if (!obs || !theta) return fail(PFB200_EINVAL, "pfb200_configure: obs and theta are required");
+  const int n_inj = (inj_z0 != nullptr) + (inj_u != nullptr) + (inj_z != nullptr) + (inj_u_final != nullptr);
+  if (n_inj != 0 && n_inj != 4)
+    return fail(PFB200_EINVAL, "pfb200_configure: injected randomness needs all of inj_z0, inj_u, inj_z, inj_u_final");
+  const bool inject = n_inj == 4;
+  const bool history = (flags & PFB200_FLAG_STORE_HISTORY) != 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+
+  // ---- launch geometry
+  const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
+  int bps = 0;
+  const size_t smem_max = (size_t)(kChunk + 1024) * sizeof(double);
+  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem_max));
+  if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM");
+  h->blocks_per_sm = bps;
+  const int capacity = bps * h->num_sms;
+  int G;
+  if (h->opt_ctas_per_filter > 0) {
+    G = (int)h->opt_ctas_per_filter;
+  } else if (B == 1) {
+    G = (N + kBlock - 1) / kBlock;
+  } else {
+    G = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
+  }
+  if (G > capacity) G = capacity;
+  if (G > 1024) G = 1024;
+  if (G < 1) G = 1;
+  int per = (N + G - 1) / G;
+  G = (N + per - 1) / per;  // no empty CTAs
+  int n_groups;
+  if (history) {
+    n_groups = B;
+    if (G > 1 && (long long)B * G > capacity)
+      return fail(PFB200_EINVAL, "pfb200_configure: STORE_HISTORY with %d filters x %d CTAs exceeds the %d co-resident CTAs", B, G, capacity);
+  } else {
+    n_groups = capacity / G;
+    if (n_groups > B) n_groups = B;
+    if (h->opt_max_groups > 0 && n_groups > h->opt_max_groups) n_groups = (int)h->opt_max_groups;
+    if (n_groups < 1) n_groups = 1;
+  }
+  h->cooperative = G > 1;
+  h->smem_bytes = (size_t)(kChunk + G) * sizeof(double);
+  h->n_ws = history ? B : n_groups;
+
+  DeviceProblem& p = h->prob;
+  p = DeviceProblem{};
+  p.N = N; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per;
+  p.RX = history ? T + 1 : L + 2;
+  p.RA = history ? T + 1 : L + 1;
+  p.RW = history ? T + 1 : 2;
+  p.do_smoother = do_smoother ? 1 : 0;
+  p.gen_init = generate_initial_state ? 1 : 0;
+  p.resampling = resampling;
+  p.svl_obs_model = (flags & PFB200_FLAG_SVL_OBS_MODEL) ? 1 : 0;
+  p.inject = inject ? 1 : 0;
+  p.inject_per_filter = (flags & PFB200_FLAG_INJECT_PER_FILTER) ? 1 : 0;
+  p.obs_per_filter = (flags & PFB200_FLAG_OBS_PER_FILTER) ? 1 : 0;
+  p.ws_per_filter = history ? 1 : 0;
+  p.initial_state = initial_state;
+  p.seed = seed;
+  p.spin_limit = h->opt_spin_limit;
+  h->flags = flags;
+
+  // ---- buffers
+  const size_t T1 = (size_t)T + 1;
+  const size_t n_obs_rows = p.obs_per_filter ? B : 1;
+  const size_t n_injr = p.inject_per_filter ? B : 1;
+  const size_t u_row = resampling == PFB200_RESAMPLE_STRATIFIED ? (size_t)N : 1;
+  CUDA_TRY(h->obs.reserve(n_obs_rows * T1 * 8));
+  CUDA_TRY(h->consts.reserve((size_t)B * kNumConsts * 8));
+  CUDA_TRY(h->evals.reserve((size_t)B * 8));
+  if (inject) {
+    CUDA_TRY(h->inj_z0.reserve(n_injr * N * 8));
+    CUDA_TRY(h->inj_u.reserve(n_injr * T1 * u_row * 8));
+    CUDA_TRY(h->inj_z.reserve(n_injr * T1 * N * 8));
+    CUDA_TRY(h->inj_uf.reserve(n_injr * 8));
+  }
+  CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * N * real_sz));
+  CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * N * real_sz));
+  CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * N * 4));
+  CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
+  CUDA_TRY(h->xflag.reserve((size_t)n_groups * 2 * G * 4));
+  CUDA_TRY(h->abortf.reserve(16));
+  CUDA_TRY(h->stat_m.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->stat_S.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->filt_part.reserve((size_t)B * T1 * G * 8));
+  CUDA_TRY(h->smo_part.reserve((size_t)B * T1 * G * (P + 1) * 8));
+  CUDA_TRY(h->traj_k.reserve((size_t)B * 4));
+  CUDA_TRY(h->traj_idx.reserve((size_t)B * 4));
+  CUDA_TRY(h->ll_terms.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->log_like.reserve((size_t)B * 8));
+  CUDA_TRY(h->filt.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->smo.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->grad.reserve((size_t)B * P * T1 * 8));
+  CUDA_TRY(h->traj.reserve((size_t)B * T1 * 8));
+
+  p.obs = h->obs.as<double>();
+  p.consts = h->consts.as<double>();
+  p.eval_ids = h->evals.as<unsigned long long>();
+  p.inj_z0 = h->inj_z0.as<double>();
+  p.inj_u = h->inj_u.as<double>();
+  p.inj_z = h->inj_z.as<double>();
+  p.inj_u_final = h->inj_uf.as<double>();
+  p.x_ring = h->x_ring.ptr;
+  p.logw = h->logw.ptr;
+  p.anc_ring = h->anc.as<int>();
+  p.xval = h->xval.as<double>();
+  p.xflag = h->xflag.as<unsigned>();
+  p.abort_flag = h->abortf.as<int>();
+  p.stat_m = h->stat_m.as<double>();
+  p.stat_S = h->stat_S.as<double>();
+  p.filt_part = h->filt_part.as<double>();
+  p.smo_part = h->smo_part.as<double>();
+  p.traj_k = h->traj_k.as<int>();
+  p.traj_idx = h->traj_idx.as<int>();
+
+  // ---- uploads
+  CUDA_TRY(cudaMemcpyAsync(h->obs.ptr, obs, n_obs_rows * T1 * 8, cudaMemcpyHostToDevice, h->stream));
+  if (inject) {
+    CUDA_TRY(cudaMemcpyAsync(h->inj_z0.ptr, inj_z0, n_injr * N * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->inj_u.ptr, inj_u, n_injr * T1 * u_row * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->inj_z.ptr, inj_z, n_injr * T1 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->inj_uf.ptr, inj_u_final, n_injr * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = upload_params(h, theta, seed, eval_ids);
+  if (rc) return rc;
+  h->configured = true;
+  return PFB200_OK;
+}
+
+int pfb200_update_params(pfb200_handle* h, const double* theta, uint64_t seed, const uint64_t* eval_ids) {
+  if (!h || !h->configured) return fail(PFB200_ESTATE, "pfb200_update_params: handle is not configured");
+  if (!theta) return fail(PFB200_EINVAL, "pfb200_update_params: theta is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return upload_params(h, theta, seed, eval_ids);
+}
+
+int pfb200_execute(pfb200_handle* h) {
+  if (!h || !h->configured) return fail(PFB200_ESTATE, "pfb200_execute: handle is not configured");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceProblem& p = h->prob;
+  const size_t T1 = (size_t)p.T + 1;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->xflag.ptr, 0, (size_t)p.n_groups * 2 * p.G * 4, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
+  const dim3 grid(p.n_groups * p.G), block(kBlock);
+  if (h->cooperative) {
+    void* args[] = {&p};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)h->kernel, grid, block, args, h->smem_bytes, h->stream));
+  } else {
+    h->kernel<<<grid, block, h->smem_bytes, h->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
+  FinalizeArgs fa{};
+  fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G; fa.do_smoother = p.do_smoother;
+  fa.stat_m = p.stat_m; fa.stat_S = p.stat_S; fa.filt_part = p.filt_part; fa.smo_part = p.smo_part;
+  fa.ll_terms = h->ll_terms.as<double>(); fa.log_like = h->log_like.as<double>();
+  fa.filt = h->filt.as<double>(); fa.smo = h->smo.as<double>(); fa.grad = h->grad.as<double>();
+  pf_finalize_kernel<<<p.B, 256, 0, h->stream>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  if (h->flags & PFB200_FLAG_STORE_HISTORY) {
+    if (h->dtype == PFB200_F64)
+      pf_trajectory_kernel<double><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<double>(), p.traj_idx, h->traj.as<double>(), p.N, (int)T1);
+    else
+      pf_trajectory_kernel<float><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<float>(), p.traj_idx, h->traj.as<double>(), p.N, (int)T1);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  h->executed = true;
+  h->timed = true;
+  return PFB200_OK;
+}
+
+int pfb200_synchronize(pfb200_handle* h) {
+  if (!h) return fail(PFB200_EINVAL, "pfb200_synchronize: NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->executed) {
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, h->abortf.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(PFB200_ETIMEOUT, "pfb200: device-side abort: an inter-CTA exchange exceeded spin_limit");
+  }
+  return PFB200_OK;
+}
+
+int pfb200_last_execute_ms(pfb200_handle* h, float* ms) {
+  if (!h || !ms) return fail(PFB200_EINVAL, "pfb200_last_execute_ms: NULL argument");
+  if (!h->timed) return fail(PFB200_ESTATE, "pfb200_last_execute_ms: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return PFB200_OK;
+}
+
+static int d2h(pfb200_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!dst) return PFB200_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return PFB200_OK;
+}
+
+int pfb200_fetch(pfb200_handle* h, double* log_like, double* filt, double* smo, double* grad_terms,
+                 int32_t* traj_index, double* traj) {
+  if (!h || !h->executed) return fail(PFB200_ESTATE, "pfb200_fetch: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const DeviceProblem& p = h->prob;
+  const size_t T1 = (size_t)p.T + 1, B = p.B;
+  int rc;
+  if ((rc = d2h(h, log_like, h->log_like.ptr, B * 8))) return rc;
+  if ((rc = d2h(h, filt, h->filt.ptr, B * T1 * 8))) return rc;
+  if (p.do_smoother) {
+    if ((rc = d2h(h, smo, h->smo.ptr, B * T1 * 8))) return rc;
+    if ((rc = d2h(h, grad_terms, h->grad.ptr, B * p.P * T1 * 8))) return rc;
+  }
+  if ((rc = d2h(h, traj_index, h->traj_idx.ptr, B * 4))) return rc;
+  const bool history = (h->flags & PFB200_FLAG_STORE_HISTORY) != 0;
+  if (history && (rc = d2h(h, traj, h->traj.ptr, B * T1 * 8))) return rc;
+  rc = pfb200_synchronize(h);
+  if (rc) return rc;
+  if (!p.do_smoother) {
+    if (smo) for (size_t i = 0; i < B * T1; ++i) smo[i] = 0.0;
+    if (grad_terms) for (size_t i = 0; i < B * p.P * T1; ++i) grad_terms[i] = 0.0;
+  }
+  if (!history && traj) for (size_t i = 0; i < B * T1; ++i) traj[i] = NAN;
+  return PFB200_OK;
+}
+
+int pfb200_fetch_steps(pfb200_handle* h, double* ll_terms, double* max_logw, double* sum_w) {
+  if (!h || !h->executed) return fail(PFB200_ESTATE, "pfb200_fetch_steps: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->prob.B * (h->prob.T + 1) * 8;
+  int rc;
+  if ((rc = d2h(h, ll_terms, h->ll_terms.ptr, n))) return rc;
+  if ((rc = d2h(h, max_logw, h->stat_m.ptr, n))) return rc;
+  if ((rc = d2h(h, sum_w, h->stat_S.ptr, n))) return rc;
+  return pfb200_synchronize(h);
+}
+
+int pfb200_fetch_history(pfb200_handle* h, double* particles, double* log_weights, int32_t* ancestors) {
+  if (!h || !h->executed) return fail(PFB200_ESTATE, "pfb200_fetch_history: nothing executed yet");
+  if (!(h->flags & PFB200_FLAG_STORE_HISTORY))
+    return fail(PFB200_ESTATE, "pfb200_fetch_history: configure with PFB200_FLAG_STORE_HISTORY");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const DeviceProblem& p = h->prob;
+  const size_t n = (size_t)p.B * (p.T + 1) * p.N;
+  int rc;
+  if (h->dtype == PFB200_F64) {
+    if ((rc = d2h(h, particles, h->x_ring.ptr, n * 8))) return rc;
+    if ((rc = d2h(h, log_weights, h->logw.ptr, n * 8))) return rc;
+  } else {
+    CUDA_TRY(h->scratch.reserve(n * 8));
+    if (particles) {
+      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->x_ring.as<float>(), h->scratch.as<double>(), n);
+      if ((rc = d2h(h, particles, h->scratch.ptr, n * 8))) return rc;
+    }
+    if (log_weights) {
+      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->logw.as<float>(), h->scratch.as<double>(), n);
+      if ((rc = d2h(h, log_weights, h->scratch.ptr, n * 8))) return rc;
+    }
+  }
+  if ((rc = d2h(h, ancestors, h->anc.ptr, n * 4))) return rc;
+  return pfb200_synchronize(h);
+}
+
+int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, int fixed_lag,
+               int do_smoother, int generate_initial_state, double initial_state, int resampling,
+               unsigned flags, const double* obs, const double* theta, uint64_t seed,
+               const uint64_t* eval_ids, const double* inj_z0, const double* inj_u,
+               const double* inj_z, const double* inj_u_final, double* log_like, double* filt,
+               double* smo, double* grad_terms, int32_t* traj_index, double* traj) {
+  int rc = pfb200_configure(h, n_filters, no_particles, no_obs, fixed_lag, do_smoother, generate_initial_state,
+                            initial_state, resampling, flags, obs, theta, seed, eval_ids, inj_z0, inj_u, inj_z,
+                            inj_u_final);
+  if (rc) return rc;
+  if ((rc = pfb200_execute(h))) return rc;
+  return pfb200_fetch(h, log_like, filt, smo, grad_terms, traj_index, traj);
+}
+
+int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int n, double* z) {
+  if (!h || !z || n < 1 || t < 0) return fail(PFB200_EINVAL, "pfb200_philox_normals: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->scratch.reserve((size_t)n * 8));
+  const int pairs = (n + 1) / 2;
+  pf_philox_normals_kernel<<<(pairs + 255) / 256, 256, 0, h->stream>>>(seed, eval_id, t, n, h->scratch.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(z, h->scratch.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PFB200_OK;
+}
+
+int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int count, double* u) {
+  if (!h || !u || count < 1) return fail(PFB200_EINVAL, "pfb200_philox_uniforms: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->scratch.reserve((size_t)count * 8));
+  pf_philox_uniforms_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(seed, eval_id, t, count, h->scratch.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(u, h->scratch.ptr, (size_t)count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PFB200_OK;
+}
+
+}  // extern "C"
