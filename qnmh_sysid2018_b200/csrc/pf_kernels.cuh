@@ -26,6 +26,7 @@ namespace pfb200 {
 
 struct DeviceProblem {
   int N, T, L, P;
+  int NS;        // row stride of the rings (N rounded up to 32 elements: aligned vector stores)
   int B;         // number of filters in the batch
   int G;         // CTAs per filter group
   int n_groups;  // groups resident in this launch
@@ -285,15 +286,15 @@ struct PfKernel {
       sw[k] = ok ? sh_s[jl] : 0.0;
     }
     for (int lvl = tau; lvl > i; --lvl) {
-      const int* a = ar + (size_t)(lvl % p.RA) * N;
+      const int* a = ar + (size_t)(lvl % p.RA) * p.NS;
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         nxt[k] = cur[k];
         cur[k] = ld_cg(a + cur[k]);
       }
     }
-    const Real* xi = xr + (size_t)(i % p.RX) * N;
-    const Real* xn = xr + (size_t)((i + 1) % p.RX) * N;
+    const Real* xi = xr + (size_t)(i % p.RX) * p.NS;
+    const Real* xn = xr + (size_t)((i + 1) % p.RX) * p.NS;
     const double y = __ldg(obs + i);
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -406,9 +407,10 @@ struct PfKernel {
   __device__ void run_filter(int b) {
     const int N = p.N, T = p.T, L = p.L, G = p.G, P = p.P;
     const int ws = p.ws_per_filter ? b : q;
-    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * N;
-    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * N;
-    int* ar = p.anc_ring + (size_t)ws * p.RA * N;
+    const size_t NS = (size_t)p.NS;
+    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS;
+    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS;
+    int* ar = p.anc_ring + (size_t)ws * p.RA * NS;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const unsigned long long eval_id = p.eval_ids[b];
     const size_t ib = p.inject_per_filter ? (size_t)b : 0;
@@ -447,8 +449,8 @@ struct PfKernel {
     for (int t = 1; t <= T + 1; ++t) {
       if (aborted) return;
       const int tau = t - 1;
-      const Real* x_prev = xr + (size_t)(tau % p.RX) * N;
-      const Real* lw_prev = lwr + (size_t)(tau % p.RW) * N;
+      const Real* x_prev = xr + (size_t)(tau % p.RX) * NS;
+      const Real* lw_prev = lwr + (size_t)(tau % p.RW) * NS;
       const bool final_step = (t == T + 1);
       const int i_sm = (p.do_smoother && !final_step && tau >= L) ? tau - L : -1;
 
@@ -526,9 +528,9 @@ struct PfKernel {
         }
         y_obs = __ldg(obs + t);
         y_prop = p.svl_obs_model ? __ldg(obs + t - 1) : y_obs;  // Q10
-        x_new = xr + (size_t)(t % p.RX) * N;
-        lw_new = lwr + (size_t)(t % p.RW) * N;
-        anc_new = ar + (size_t)(t % p.RA) * N;
+        x_new = xr + (size_t)(t % p.RX) * NS;
+        lw_new = lwr + (size_t)(t % p.RW) * NS;
+        anc_new = ar + (size_t)(t % p.RA) * NS;
       } else {
         u = p.inject ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
       }
@@ -578,7 +580,7 @@ struct PfKernel {
         if (g == 0 && tid == 0) {
           int k = ld_cg(p.traj_k + b);
           if (k > N - 1) k = N - 1;
-          p.traj_idx[b] = ld_cg(ar + (size_t)(T % p.RA) * N + k);
+          p.traj_idx[b] = ld_cg(ar + (size_t)(T % p.RA) * NS + k);
         }
       } else {
         mx = block_max(mx);
@@ -660,16 +662,17 @@ __global__ void __launch_bounds__(256) pf_finalize_kernel(const FinalizeArgs a) 
 
 // trajectory rows from the stored history: traj[b][t] = x[b][t][traj_idx[b]]
 template <typename Real>
-__global__ void pf_trajectory_kernel(const Real* x_hist, const int* traj_idx, double* traj, int N, int T1) {
+__global__ void pf_trajectory_kernel(const Real* x_hist, const int* traj_idx, double* traj, int NS, int T1) {
   const int b = blockIdx.x;
   for (int t = threadIdx.x; t < T1; t += blockDim.x)
-    traj[(size_t)b * T1 + t] = (double)x_hist[((size_t)b * T1 + t) * N + traj_idx[b]];
+    traj[(size_t)b * T1 + t] = (double)x_hist[((size_t)b * T1 + t) * NS + traj_idx[b]];
 }
 
 template <typename Real>
-__global__ void pf_to_double_kernel(const Real* src, double* dst, size_t n) {
+__global__ void pf_to_double_kernel(const Real* src, double* dst, size_t rows, int N, int NS) {
+  const size_t n = rows * (size_t)N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = (double)src[i];
+    dst[i] = (double)src[(i / N) * NS + (i % N)];
 }
 
 __global__ void pf_philox_normals_kernel(unsigned long long seed, unsigned long long eval_id, int t, int n, double* z) {

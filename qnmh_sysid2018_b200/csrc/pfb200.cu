@@ -322,7 +322,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per;
+  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per;
   p.RX = history ? T + 1 : L + 2;
   p.RA = history ? T + 1 : L + 1;
   p.RW = history ? T + 1 : 2;
@@ -353,9 +353,9 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     CUDA_TRY(h->inj_z.reserve(n_injr * T1 * N * 8));
     CUDA_TRY(h->inj_uf.reserve(n_injr * 8));
   }
-  CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * N * real_sz));
-  CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * N * real_sz));
-  CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * N * 4));
+  CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * p.NS * real_sz));
+  CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
+  CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
   CUDA_TRY(h->xflag.reserve((size_t)n_groups * 2 * G * 4));
   CUDA_TRY(h->abortf.reserve(16));
@@ -439,9 +439,9 @@ int pfb200_execute(pfb200_handle* h) {
   CUDA_TRY(cudaGetLastError());
   if (h->flags & PFB200_FLAG_STORE_HISTORY) {
     if (h->dtype == PFB200_F64)
-      pf_trajectory_kernel<double><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<double>(), p.traj_idx, h->traj.as<double>(), p.N, (int)T1);
+      pf_trajectory_kernel<double><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<double>(), p.traj_idx, h->traj.as<double>(), p.NS, (int)T1);
     else
-      pf_trajectory_kernel<float><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<float>(), p.traj_idx, h->traj.as<double>(), p.N, (int)T1);
+      pf_trajectory_kernel<float><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<float>(), p.traj_idx, h->traj.as<double>(), p.NS, (int)T1);
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
@@ -520,23 +520,29 @@ int pfb200_fetch_history(pfb200_handle* h, double* particles, double* log_weight
     return fail(PFB200_ESTATE, "pfb200_fetch_history: configure with PFB200_FLAG_STORE_HISTORY");
   CUDA_TRY(cudaSetDevice(h->device));
   const DeviceProblem& p = h->prob;
-  const size_t n = (size_t)p.B * (p.T + 1) * p.N;
-  int rc;
+  const size_t rows = (size_t)p.B * (p.T + 1);
+  const size_t n = rows * p.N;
   if (h->dtype == PFB200_F64) {
-    if ((rc = d2h(h, particles, h->x_ring.ptr, n * 8))) return rc;
-    if ((rc = d2h(h, log_weights, h->logw.ptr, n * 8))) return rc;
+    if (particles)
+      CUDA_TRY(cudaMemcpy2DAsync(particles, (size_t)p.N * 8, h->x_ring.ptr, (size_t)p.NS * 8, (size_t)p.N * 8, rows,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    if (log_weights)
+      CUDA_TRY(cudaMemcpy2DAsync(log_weights, (size_t)p.N * 8, h->logw.ptr, (size_t)p.NS * 8, (size_t)p.N * 8, rows,
+                                 cudaMemcpyDeviceToHost, h->stream));
   } else {
     CUDA_TRY(h->scratch.reserve(n * 8));
     if (particles) {
-      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->x_ring.as<float>(), h->scratch.as<double>(), n);
-      if ((rc = d2h(h, particles, h->scratch.ptr, n * 8))) return rc;
+      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->x_ring.as<float>(), h->scratch.as<double>(), rows, p.N, p.NS);
+      CUDA_TRY(cudaMemcpyAsync(particles, h->scratch.ptr, n * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     if (log_weights) {
-      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->logw.as<float>(), h->scratch.as<double>(), n);
-      if ((rc = d2h(h, log_weights, h->scratch.ptr, n * 8))) return rc;
+      pf_to_double_kernel<float><<<1024, 256, 0, h->stream>>>(h->logw.as<float>(), h->scratch.as<double>(), rows, p.N, p.NS);
+      CUDA_TRY(cudaMemcpyAsync(log_weights, h->scratch.ptr, n * 8, cudaMemcpyDeviceToHost, h->stream));
     }
   }
-  if ((rc = d2h(h, ancestors, h->anc.ptr, n * 4))) return rc;
+  if (ancestors)
+    CUDA_TRY(cudaMemcpy2DAsync(ancestors, (size_t)p.N * 4, h->anc.ptr, (size_t)p.NS * 4, (size_t)p.N * 4, rows,
+                               cudaMemcpyDeviceToHost, h->stream));
   return pfb200_synchronize(h);
 }
 
