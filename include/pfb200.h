@@ -124,6 +124,8 @@ int pfb200_synchronize(pfb200_handle* h);
 
 /* Device time of the most recent pfb200_execute in ms (CUDA events on the handle's stream). */
 int pfb200_last_execute_ms(pfb200_handle* h, float* ms);
+/* Device time of the persistent filter/smoother kernel alone within that execute. */
+int pfb200_last_kernel_ms(pfb200_handle* h, float* ms);
 
 /*
  * Copies results to host memory (D2H on the stream, then waits).  Any pointer may be NULL.
@@ -163,6 +165,10 @@ int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int
  * t = -1: the trajectory-draw uniform). */
 int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int count,
                            double* u);
+
+/* Debug builds (-DPFB_PROFILE) only: per-CTA cycle counters of 12 phases of a time step, summed
+ * over the launch; out[cta][12].  Returns the number of CTAs written (or a negative error). */
+int pfb200_debug_profile(pfb200_handle* h, long long* out, int max_ctas);
 
 #ifdef __cplusplus
 }

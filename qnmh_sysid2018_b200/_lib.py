@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libpfb200.so")
+LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(HERE, "csrc", "libpfb200.so")  # env: tuning builds
 
 MODEL_LGSS, MODEL_SV, MODEL_SVL = 0, 1, 2
 F64, F32 = 0, 1
@@ -37,12 +37,14 @@ SIGNATURES = {
     "pfb200_execute": (C.c_int, [_H]),
     "pfb200_synchronize": (C.c_int, [_H]),
     "pfb200_last_execute_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "pfb200_last_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "pfb200_fetch": (C.c_int, [_H, _dp, _dp, _dp, _dp, _ip, _dp]),
     "pfb200_fetch_steps": (C.c_int, [_H, _dp, _dp, _dp]),
     "pfb200_fetch_history": (C.c_int, [_H, _dp, _dp, _ip]),
     "pfb200_run": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                              C.c_uint, _dp, _dp, C.c_uint64, _up, _dp, _dp, _dp, _dp,
                              _dp, _dp, _dp, _dp, _ip, _dp]),
+    "pfb200_debug_profile": (C.c_int, [_H, C.POINTER(C.c_longlong), C.c_int]),
     "pfb200_philox_normals": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),
     "pfb200_philox_uniforms": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),
 }

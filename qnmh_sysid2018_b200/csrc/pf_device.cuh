@@ -198,6 +198,47 @@ struct ModelOps<MODEL, float> {
 };
 
 // ------------------------------------------------------------------------------------------
+// exp(x) for x <= 0 (shifted log-weights): round-to-nearest range reduction x = k ln2 + r,
+// |r| <= ln2/2, degree-13 Taylor polynomial (truncation < 5e-18), scaling by 2^k through the
+// exponent bits.  Results below 2^-1021 (weights 1e-307 times the maximum) flush to zero; NaN
+// propagates.  About 1 ulp, ~4x fewer instructions than the general-purpose exp().
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double t = x * 1.4426950408889634074;
+  if (!(t > -1021.0)) return (t == t) ? 0.0 : t;  // underflow -> 0, NaN -> NaN
+  const int k = __double2int_rn(t);
+  const double kf = (double)k;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;           // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
+  q = fma(q, r, 1.3888888888888889e-03);       // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  return q * __hiloint2double((k + 1023) << 20, 0);
+}
+
+template <typename Real>
+__device__ __forceinline__ double shifted_weight(Real logw, double m);
+template <>
+__device__ __forceinline__ double shifted_weight<double>(double logw, double m) {
+  return exp_nonpos(logw - m);
+}
+template <>
+__device__ __forceinline__ double shifted_weight<float>(float logw, double m) {
+  return (double)__expf(logw - (float)m);
+}
+
+// ------------------------------------------------------------------------------------------
 // Memory-ordering helpers for the inter-CTA exchange (gpu scope).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {

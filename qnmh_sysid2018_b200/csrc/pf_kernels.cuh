@@ -24,6 +24,12 @@
 
 namespace pfb200 {
 
+#ifdef PFB_PROFILE
+#define PFB_TICK(slot) do { const long long now__ = clock64(); prof_acc[slot] += now__ - prof_t; prof_t = now__; } while (0)
+#else
+#define PFB_TICK(slot) do { } while (0)
+#endif
+
 struct DeviceProblem {
   int N, T, L, P;
   int NS;        // row stride of the rings (N rounded up to 32 elements: aligned vector stores)
@@ -56,6 +62,7 @@ struct DeviceProblem {
   double* smo_part;   // [B][T+1][G][P+1]
   int* traj_k;        // [B]
   int* traj_idx;      // [B]
+  long long* prof;    // [grid][8] per-phase cycle counters (PFB_PROFILE builds only)
 };
 
 template <int BLOCK, int ITEMS>
@@ -79,13 +86,20 @@ struct PfKernel {
   double* sh_red;  // [kWarps][kRedK]
   double* sh_c;    // [kNumConsts]
   const int tid, lane, warp, g, q;
+  const bool pow2N;
+  const double invN;
   unsigned epoch;
   bool aborted;
+#ifdef PFB_PROFILE
+  long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = 0;
+#endif
 
   __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst)
       : p(prob), sh_s(smem), sh_x(smem + C::kChunk), sh_red(red), sh_c(cst), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g(blockIdx.x % prob.G),
-        q(blockIdx.x / prob.G), epoch(0), aborted(false) {}
+        q(blockIdx.x / prob.G), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
+        epoch(0), aborted(false) {}
 
   // ---- inter-CTA exchange: every CTA of the group contributes one double; on return
   //      sh_x[0..G) holds all contributions (same bits in every CTA).
@@ -117,7 +131,6 @@ struct PfKernel {
       }
       sh_x[i] = ld_cg(val + i);
     }
-    __threadfence();
     aborted = __syncthreads_or(aborted ? 1 : 0) != 0;  // block-uniform
   }
 
@@ -232,8 +245,7 @@ struct PfKernel {
       const int jl = k * BLOCK + tid;
       double s = 0.0;
       if (jl < len) {
-        const double l = (double)ld_cg(lw + c0 + jl);
-        s = exp(l - m);
+        s = shifted_weight<Real>(ld_cg(lw + c0 + jl), m);
         if (accF) f += s * (double)ld_cg(xg + c0 + jl);
       }
       sh_s[jl] = s;
@@ -274,39 +286,40 @@ struct PfKernel {
   //      (standard.py:146-169); s[j] is read from the (unscanned) tile in sh_s.
   __device__ void smooth_chunk(const Real* xr, const int* ar, const double* obs, int tau, int i,
                                int c0, int len, double (&acc)[kMaxParams + 1]) {
-    const int N = p.N;
+    const size_t NS = (size_t)p.NS;
     int cur[ITEMS], nxt[ITEMS];
-    double sw[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
       const int jl = k * BLOCK + tid;
-      const bool ok = jl < len;
-      cur[k] = ok ? c0 + jl : 0;
+      cur[k] = (jl < len) ? c0 + jl : c0;
       nxt[k] = cur[k];
-      sw[k] = ok ? sh_s[jl] : 0.0;
     }
+    int slot = tau % p.RA;
     for (int lvl = tau; lvl > i; --lvl) {
-      const int* a = ar + (size_t)(lvl % p.RA) * p.NS;
+      const int* a = ar + (size_t)slot * NS;
+      slot = (slot == 0) ? p.RA - 1 : slot - 1;
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         nxt[k] = cur[k];
         cur[k] = ld_cg(a + cur[k]);
       }
     }
-    const Real* xi = xr + (size_t)(i % p.RX) * p.NS;
-    const Real* xn = xr + (size_t)((i + 1) % p.RX) * p.NS;
+    const Real* xi = xr + (size_t)(i % p.RX) * NS;
+    const Real* xn = xr + (size_t)((i + 1) % p.RX) * NS;
     const double y = __ldg(obs + i);
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
+      const int jl = k * BLOCK + tid;
+      const double sw = (jl < len) ? sh_s[jl] : 0.0;
       const Real xc = ld_cg(xi + cur[k]);
       const Real xnext = ld_cg(xn + nxt[k]);
       double gr[kMaxParams];
       Ops::gradient(sh_c, xnext, xc, y, gr);
-      const double t0 = (double)xc * sw[k];
+      const double t0 = (double)xc * sw;
       if (!isnan(t0)) acc[0] += t0;  // np.nansum
 #pragma unroll
       for (int pp = 0; pp < kMaxParams; ++pp) {
-        const double tp = gr[pp] * sw[k];
+        const double tp = gr[pp] * sw;
         if (!isnan(tp)) acc[1 + pp] += tp;
       }
     }
@@ -317,9 +330,11 @@ struct PfKernel {
                                              unsigned long long eval_id) const {
     if (p.resampling == 1) {
       u = p.inject ? ld_cg(inj_u_t + n) : philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)n);
-      return __ddiv_rn(__dadd_rn(u, (double)n), (double)p.N);
+      const double a = __dadd_rn(u, (double)n);
+      return pow2N ? __dmul_rn(a, invN) : __ddiv_rn(a, (double)p.N);
     }
-    return __ddiv_rn(__dadd_rn((double)n, u), (double)p.N);
+    const double a = __dadd_rn((double)n, u);
+    return pow2N ? __dmul_rn(a, invN) : __ddiv_rn(a, (double)p.N);  // x * 2^-k == x / 2^k exactly
   }
 
   // smallest n in [0, N] with NOT (position(n) < c)
@@ -344,61 +359,76 @@ struct PfKernel {
     return lo;
   }
 
-  // ---- children of the CDF tile in sh_s: resample + propagate + weight (phase B)
+  // parent (tile-local) of a child at `pos`, knowing that it is >= lo (children are monotone)
+  __device__ __forceinline__ int next_parent(double pos, int lo, int len) const {
+    if (sh_s[lo] > pos) return lo;
+    if (lo + 1 < len && sh_s[lo + 1] > pos) return lo + 1;
+    return upper_bound_tile(pos, (lo + 2 < len) ? lo + 2 : len, len);
+  }
+
+  // ---- children of the CDF tile in sh_s: resample + propagate + weight (phase B).  A thread owns
+  //      4 consecutive children: one binary search, then short forward merges; 32-byte stores.
   __device__ void children_chunk(const Real* x_prev, Real* x_new, Real* lw_new, int* anc_new,
                                  const double* inj_z_t, const double* inj_u_t, int t, double u,
                                  unsigned long long eval_id, double y_prop, double y_obs, int c0,
                                  int len, int n_lo, int n_hi, double& mx) {
-    const int p0 = n_lo >> 1, p1 = (n_hi + 1) >> 1;
-    for (int pp = p0 + tid; pp < p1; pp += BLOCK) {
-      const int na = 2 * pp, nb = na + 1;
-      const bool va = na >= n_lo && na < n_hi;
-      const bool vb = nb >= n_lo && nb < n_hi;
-      Real za, zb;
+    const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
+    for (int qq = q0 + tid; qq < q1; qq += BLOCK) {
+      const int nb = 4 * qq;
+      Real z[4];
       if (p.inject) {
-        za = va ? (Real)ld_cg(inj_z_t + na) : (Real)0;
-        zb = vb ? (Real)ld_cg(inj_z_t + nb) : (Real)0;
-      } else {
-        philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)pp, za, zb);
-      }
-      int ja = 0, jb = 0;
-      if (va) {
-        const double pos = position(na, u, t, inj_u_t, eval_id);
-        ja = upper_bound_tile(pos, 0, len);
-        if (ja > len - 1) ja = len - 1;
-      }
-      if (vb) {
-        const double pos = position(nb, u, t, inj_u_t, eval_id);
-        int lo = va ? ja : 0;
-        if (sh_s[lo] > pos) jb = lo;
-        else if (lo + 1 < len && sh_s[lo + 1] > pos) jb = lo + 1;
-        else jb = upper_bound_tile(pos, (lo + 2 < len) ? lo + 2 : len, len);
-        if (jb > len - 1) jb = len - 1;
-      }
-      Real xa = 0, xb = 0, la = 0, lb = 0;
-      if (va) {
-        xa = Ops::propagate(sh_c, ld_cg(x_prev + c0 + ja), za, y_prop);
-        la = Ops::logweight(sh_c, xa, y_obs);
-        mx = fmax(mx, (double)la);
-      }
-      if (vb) {
-        xb = Ops::propagate(sh_c, ld_cg(x_prev + c0 + jb), zb, y_prop);
-        lb = Ops::logweight(sh_c, xb, y_obs);
-        mx = fmax(mx, (double)lb);
-      }
-      if (va && vb) {
-        if (sizeof(Real) == 8) {
-          *reinterpret_cast<double2*>(x_new + na) = make_double2((double)xa, (double)xb);
-          *reinterpret_cast<double2*>(lw_new + na) = make_double2((double)la, (double)lb);
-        } else {
-          *reinterpret_cast<float2*>(x_new + na) = make_float2((float)xa, (float)xb);
-          *reinterpret_cast<float2*>(lw_new + na) = make_float2((float)la, (float)lb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = nb + e;
+          z[e] = (n >= n_lo && n < n_hi) ? (Real)ld_cg(inj_z_t + n) : (Real)0;
         }
-        *reinterpret_cast<int2*>(anc_new + na) = make_int2(c0 + ja, c0 + jb);
-      } else if (va) {
-        x_new[na] = xa; lw_new[na] = la; anc_new[na] = c0 + ja;
-      } else if (vb) {
-        x_new[nb] = xb; lw_new[nb] = lb; anc_new[nb] = c0 + jb;
+      } else {
+        philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq), z[0], z[1]);
+        philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq + 1), z[2], z[3]);
+      }
+      int j[4];
+      int lo = -1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = nb + e;
+        j[e] = 0;
+        if (n >= n_lo && n < n_hi) {
+          const double pos = position(n, u, t, inj_u_t, eval_id);
+          lo = (lo < 0) ? upper_bound_tile(pos, 0, len) : next_parent(pos, lo, len);
+          if (lo > len - 1) lo = len - 1;
+          j[e] = lo;
+        }
+      }
+      Real xv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = nb + e;
+        xv[e] = 0; lv[e] = 0;
+        if (n >= n_lo && n < n_hi) {
+          xv[e] = Ops::propagate(sh_c, ld_cg(x_prev + c0 + j[e]), z[e], y_prop);
+          lv[e] = Ops::logweight(sh_c, xv[e], y_obs);
+          mx = fmax(mx, (double)lv[e]);
+        }
+      }
+      if (nb >= n_lo && nb + 3 < n_hi) {
+        if (sizeof(Real) == 8) {
+          double2* xd = reinterpret_cast<double2*>(x_new + nb);
+          double2* ld = reinterpret_cast<double2*>(lw_new + nb);
+          xd[0] = make_double2((double)xv[0], (double)xv[1]);
+          xd[1] = make_double2((double)xv[2], (double)xv[3]);
+          ld[0] = make_double2((double)lv[0], (double)lv[1]);
+          ld[1] = make_double2((double)lv[2], (double)lv[3]);
+        } else {
+          *reinterpret_cast<float4*>(x_new + nb) = make_float4((float)xv[0], (float)xv[1], (float)xv[2], (float)xv[3]);
+          *reinterpret_cast<float4*>(lw_new + nb) = make_float4((float)lv[0], (float)lv[1], (float)lv[2], (float)lv[3]);
+        }
+        *reinterpret_cast<int4*>(anc_new + nb) = make_int4(c0 + j[0], c0 + j[1], c0 + j[2], c0 + j[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = nb + e;
+          if (n >= n_lo && n < n_hi) { x_new[n] = xv[e]; lw_new[n] = lv[e]; anc_new[n] = c0 + j[e]; }
+        }
       }
     }
   }
@@ -454,6 +484,9 @@ struct PfKernel {
       const bool final_step = (t == T + 1);
       const int i_sm = (p.do_smoother && !final_step && tau >= L) ? tau - L : -1;
 
+#ifdef PFB_PROFILE
+      prof_t = clock64();
+#endif
       // ---------------- phase A
       double accF = 0.0, A = 0.0, chunk_total = 0.0;
       double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -461,13 +494,16 @@ struct PfKernel {
         const int c0 = j_begin + c * C::kChunk;
         const int len = min(C::kChunk, j_end - c0);
         load_chunk(lw_prev, x_prev, c0, len, m, &accF);
+        PFB_TICK(8);
         if (i_sm >= 0) {
           smooth_chunk(xr, ar, obs, tau, i_sm, c0, len, acc);
           __syncthreads();
         }
+        PFB_TICK(9);
         chunk_total = scan_chunk();
         A += chunk_total;
       }
+      PFB_TICK(0);
       {
         double red[kMaxParams + 2] = {accF, acc[0], acc[1], acc[2], acc[3], acc[4]};
         block_sum(red);
@@ -479,7 +515,9 @@ struct PfKernel {
           }
         }
       }
+      PFB_TICK(1);
       exchange(A);
+      PFB_TICK(2);
       double Pg, Pg1, S;
       xchg_prefix(Pg, Pg1, S);
       if (g == 0 && tid == 0) {
@@ -534,8 +572,10 @@ struct PfKernel {
       } else {
         u = p.inject ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
       }
-      const int n_begin = final_step ? 0 : ((g == 0) ? 0 : lower_bound_child(Pg / S, u, t, inj_u_t, eval_id));
-      const int n_end = final_step ? 0 : (last_cta ? N : lower_bound_child(Pg1 / S, u, t, inj_u_t, eval_id));
+      const double invS = 1.0 / S;  // the CDF is (prefix sum) * (1/S) everywhere, boundaries included
+      const int n_begin = final_step ? 0 : ((g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg, invS), u, t, inj_u_t, eval_id));
+      const int n_end = final_step ? 0 : (last_cta ? N : lower_bound_child(__dmul_rn(Pg1, invS), u, t, inj_u_t, eval_id));
+      PFB_TICK(3);
       double mx = -INFINITY;
       int n_cursor = n_begin, traj_cnt = 0;
       double base = Pg;
@@ -550,9 +590,10 @@ struct PfKernel {
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
           const int jl = k * BLOCK + tid;
-          if (jl < len) sh_s[jl] = __ddiv_rn(__dadd_rn(base, sh_s[jl]), S);
+          if (jl < len) sh_s[jl] = __dmul_rn(__dadd_rn(base, sh_s[jl]), invS);
         }
         __syncthreads();
+        PFB_TICK(10);
         if (final_step) {
           // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
 #pragma unroll
@@ -564,7 +605,7 @@ struct PfKernel {
           const double next_base = base + chunk_total;
           int n_hi = n_end;
           if (c + 1 < n_chunks) {
-            n_hi = lower_bound_child(next_base / S, u, t, inj_u_t, eval_id);
+            n_hi = lower_bound_child(__dmul_rn(next_base, invS), u, t, inj_u_t, eval_id);
             n_hi = max(n_cursor, min(n_hi, n_end));
           }
           children_chunk(x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
@@ -583,16 +624,20 @@ struct PfKernel {
           p.traj_idx[b] = ld_cg(ar + (size_t)(T % p.RA) * NS + k);
         }
       } else {
+        PFB_TICK(4);
         mx = block_max(mx);
+        PFB_TICK(5);
         exchange(mx);
+        PFB_TICK(6);
         m = xchg_max();
+        PFB_TICK(7);
       }
     }
   }
 };
 
-template <int MODEL, typename Real, int BLOCK, int ITEMS>
-__global__ void __launch_bounds__(BLOCK) pf_persistent_kernel(const DeviceProblem prob) {
+template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const DeviceProblem prob) {
   extern __shared__ double pf_smem[];
   __shared__ double sh_red[(BLOCK / 32) * (kMaxParams + 2) + 40];
   __shared__ double sh_c[kNumConsts];
@@ -601,6 +646,10 @@ __global__ void __launch_bounds__(BLOCK) pf_persistent_kernel(const DeviceProble
     k.run_filter(b);
     if (k.aborted) return;
   }
+#ifdef PFB_PROFILE
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 12; ++i) prob.prof[(size_t)blockIdx.x * 12 + i] = k.prof_acc[i];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -64,8 +64,18 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-constexpr int kBlock = 512;
-constexpr int kItems = 7;
+#ifndef PFB_BLOCK
+#define PFB_BLOCK 512
+#endif
+#ifndef PFB_ITEMS
+#define PFB_ITEMS 7
+#endif
+#ifndef PFB_MINB
+#define PFB_MINB 1
+#endif
+constexpr int kBlock = PFB_BLOCK;
+constexpr int kItems = PFB_ITEMS;
+constexpr int kMinB = PFB_MINB;
 constexpr int kChunk = kBlock * kItems;
 
 typedef void (*KernelFn)(const DeviceProblem);
@@ -73,9 +83,11 @@ typedef void (*KernelFn)(const DeviceProblem);
 template <typename Real>
 KernelFn kernel_for_model(int model) {
   switch (model) {
-    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems>;
-    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems>;
-    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems>;
+    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems, kMinB>;
+#ifndef PFB_LGSS_ONLY
+    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems, kMinB>;
+    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems, kMinB>;
+#endif
   }
   return nullptr;
 }
@@ -120,7 +132,7 @@ struct pfb200_handle {
   int blocks_per_sm = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false;
   KernelFn kernel = nullptr;
   // options
@@ -139,7 +151,7 @@ struct pfb200_handle {
   DevBuf obs, consts, evals, inj_z0, inj_u, inj_z, inj_uf;
   DevBuf x_ring, logw, anc, xval, xflag, abortf;
   DevBuf stat_m, stat_S, filt_part, smo_part, traj_k, traj_idx;
-  DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch;
+  DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch, prof;
   std::vector<double> h_consts;
   std::vector<unsigned long long> h_evals;
 };
@@ -188,6 +200,8 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   h->stream = h->own_stream;
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
+  CUDA_TRY(cudaEventCreate(&h->evk0));
+  CUDA_TRY(cudaEventCreate(&h->evk1));
   *out = h;
   return PFB200_OK;
 }
@@ -199,10 +213,12 @@ int pfb200_destroy(pfb200_handle* h) {
   DevBuf* bufs[] = {&h->obs, &h->consts, &h->evals, &h->inj_z0, &h->inj_u, &h->inj_z, &h->inj_uf, &h->x_ring,
                     &h->logw, &h->anc, &h->xval, &h->xflag, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
                     &h->smo_part, &h->traj_k, &h->traj_idx, &h->ll_terms, &h->log_like, &h->filt, &h->smo,
-                    &h->grad, &h->traj, &h->scratch};
+                    &h->grad, &h->traj, &h->scratch, &h->prof};
   for (DevBuf* b : bufs) b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evk0) cudaEventDestroy(h->evk0);
+  if (h->evk1) cudaEventDestroy(h->evk1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return PFB200_OK;
@@ -371,6 +387,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->smo.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->grad.reserve((size_t)B * P * T1 * 8));
   CUDA_TRY(h->traj.reserve((size_t)B * T1 * 8));
+  CUDA_TRY(h->prof.reserve((size_t)n_groups * G * 12 * 8));
 
   p.obs = h->obs.as<double>();
   p.consts = h->consts.as<double>();
@@ -391,6 +408,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.smo_part = h->smo_part.as<double>();
   p.traj_k = h->traj_k.as<int>();
   p.traj_idx = h->traj_idx.as<int>();
+  p.prof = h->prof.as<long long>();
 
   // ---- uploads
   CUDA_TRY(cudaMemcpyAsync(h->obs.ptr, obs, n_obs_rows * T1 * 8, cudaMemcpyHostToDevice, h->stream));
@@ -423,6 +441,7 @@ int pfb200_execute(pfb200_handle* h) {
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
   const dim3 grid(p.n_groups * p.G), block(kBlock);
+  CUDA_TRY(cudaEventRecord(h->evk0, h->stream));
   if (h->cooperative) {
     void* args[] = {&p};
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)h->kernel, grid, block, args, h->smem_bytes, h->stream));
@@ -430,6 +449,7 @@ int pfb200_execute(pfb200_handle* h) {
     h->kernel<<<grid, block, h->smem_bytes, h->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
   }
+  CUDA_TRY(cudaEventRecord(h->evk1, h->stream));
   FinalizeArgs fa{};
   fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G; fa.do_smoother = p.do_smoother;
   fa.stat_m = p.stat_m; fa.stat_S = p.stat_S; fa.filt_part = p.filt_part; fa.smo_part = p.smo_part;
@@ -468,6 +488,15 @@ int pfb200_last_execute_ms(pfb200_handle* h, float* ms) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaEventSynchronize(h->ev1));
   CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return PFB200_OK;
+}
+
+int pfb200_last_kernel_ms(pfb200_handle* h, float* ms) {
+  if (!h || !ms) return fail(PFB200_EINVAL, "pfb200_last_kernel_ms: NULL argument");
+  if (!h->timed) return fail(PFB200_ESTATE, "pfb200_last_kernel_ms: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->evk1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->evk0, h->evk1));
   return PFB200_OK;
 }
 
@@ -558,6 +587,16 @@ int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, in
   if (rc) return rc;
   if ((rc = pfb200_execute(h))) return rc;
   return pfb200_fetch(h, log_like, filt, smo, grad_terms, traj_index, traj);
+}
+
+int pfb200_debug_profile(pfb200_handle* h, long long* out, int max_ctas) {
+  if (!h || !out || !h->executed) return fail(PFB200_ESTATE, "pfb200_debug_profile: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int n = h->prob.n_groups * h->prob.G;
+  if (n > max_ctas) n = max_ctas;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(out, h->prof.ptr, (size_t)n * 12 * 8, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int n, double* z) {

@@ -138,6 +138,11 @@ class Engine(object):
         L.check(self._lib.pfb200_last_execute_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        L.check(self._lib.pfb200_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def fetch(self, out=None):
         """Returns dict(log_like (B,), filt (B,T+1), smo (B,T+1), grad_terms (B,P,T+1),
         traj_index (B,), traj (B,T+1)).  `out` may hold preallocated (e.g. pinned) arrays."""
@@ -181,6 +186,14 @@ class Engine(object):
         self.configure(*args, **kwargs)
         self.execute()
         return self.fetch()
+
+    def debug_profile(self, max_ctas=4096):
+        """(n_ctas, 12) cycle counters per phase; all zero unless built with -DPFB_PROFILE."""
+        buf = np.zeros((max_ctas, 12), dtype=np.int64)
+        n = self._lib.pfb200_debug_profile(self._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), max_ctas)
+        if n < 0:
+            L.check(n)
+        return buf[:n]
 
     def philox_normals(self, seed, eval_id, t, n):
         z = np.empty(int(n))
