@@ -1,8 +1,7 @@
 #!/bin/bash
+echo "== default"; python tools/run_once.py --T 100 2>&1 | grep "kernel ms"; python tools/run_once.py --T 100 --N 4096 --B 1024 2>&1 | grep "kernel ms"
 for so in build_variants/*.so; do
   echo "== $so"
-  PFB200_LIB=$PWD/$so python tools/run_once.py --T 200 2>&1 | tail -1
-  PFB200_LIB=$PWD/$so python tools/run_once.py --T 200 --N 65536 2>&1 | tail -1
-  PFB200_LIB=$PWD/$so python tools/run_once.py --T 200 --N 4096 --B 1024 2>&1 | tail -1
+  PFB200_LIB=$PWD/$so python tools/run_once.py --T 100 2>&1 | grep -E "kernel ms"
+  PFB200_LIB=$PWD/$so python tools/run_once.py --T 100 --N 4096 --B 1024 2>&1 | grep -E "kernel ms"
 done
-echo "== default build"; python -m pytest tests -m gpu -q 2>&1 | tail -3

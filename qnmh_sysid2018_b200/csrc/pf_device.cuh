@@ -101,6 +101,21 @@ __device__ __forceinline__ void philox_normal_pair<float>(uint64_t seed, uint64_
   z_odd = rad * s;
 }
 
+// Shared-memory access through a 32-bit shared-window address held in a register.  Indexing a
+// generic pointer to shared memory makes the compiler rematerialise the window base
+// (S2R SR_CgaCtaId + LEA) in front of every load -- in the binary-search loop that costs more
+// than the load itself -- so hot loops keep an opaque base address and use ld.shared directly.
+__device__ __forceinline__ uint32_t smem_base(const void* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // opaque: must live in a register
+  return a;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-particle model arithmetic.  The fp64 propagate / weight paths pin the reference's operation
 // order with round-to-nearest intrinsics (never contracted to FMA), so that with injected noise a
@@ -108,6 +123,25 @@ __device__ __forceinline__ void philox_normal_pair<float>(uint64_t seed, uint64_
 // ------------------------------------------------------------------------------------------
 template <int MODEL, typename Real>
 struct ModelOps;
+
+// constants read by propagate() / logweight(): loaded once per phase into registers
+template <int MODEL>
+__device__ __forceinline__ void load_step_consts(uint32_t c_addr, double (&c)[kNumConsts]) {
+#pragma unroll
+  for (int i = 0; i < kNumConsts; ++i) c[i] = 0.0;
+  c[C_MU] = lds_f64(c_addr + 8 * C_MU);
+  c[C_PHI] = lds_f64(c_addr + 8 * C_PHI);
+  if (MODEL == kModelSVL) {
+    c[C_SVRHO] = lds_f64(c_addr + 8 * C_SVRHO);
+    c[C_STDEV] = lds_f64(c_addr + 8 * C_STDEV);
+  } else {
+    c[C_SIGV] = lds_f64(c_addr + 8 * C_SIGV);
+  }
+  if (MODEL == kModelLGSS) {
+    c[C_SIGE_OR_RHO] = lds_f64(c_addr + 8 * C_SIGE_OR_RHO);
+    c[C_LOGSIGE] = lds_f64(c_addr + 8 * C_LOGSIGE);
+  }
+}
 
 template <int MODEL>
 struct ModelOps<MODEL, double> {
@@ -249,6 +283,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ int ld_relaxed_i32(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -260,6 +297,41 @@ __device__ __forceinline__ int ld_relaxed_i32(const int* p) {
 template <typename T>
 __device__ __forceinline__ T ld_cg(const T* p) {
   return __ldcg(p);
+}
+
+// L2 eviction-priority hints.  The ancestor ring is re-read on every time step for L steps while
+// particles / log-weights stream through once or twice, and the whole ring set is larger than what
+// L2 keeps: ancestors are tagged evict_last, one-shot reads of old generations evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_hint(const int* p, uint64_t pol) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_hint(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_hint(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_hint_int2(int* p, int a, int b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.s32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_int(int* p, int a, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(a), "l"(pol) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -18,7 +18,11 @@
 //   exchange 2: per-CTA max of the new log-weights -> m_t
 //
 // so neither the CDF nor the normalised weights ever touch global memory.  Generations live in
-// time-major rings: x (L+2 deep), ancestors (L+1), log-weights (2).
+// time-major rings: x (L+3 deep), ancestors (L+2), log-weights (3).
+//
+// The CDF tile of a CTA stays resident in shared memory across the two phases when it fits
+// (`tile_cap`); it is scanned in sub-chunks of BLOCK*ITEMS parents.  Larger tiles stream through
+// one sub-chunk buffer and are recomputed in phase B.
 #pragma once
 #include "pf_device.cuh"
 
@@ -29,6 +33,10 @@ namespace pfb200 {
 #else
 #define PFB_TICK(slot) do { } while (0)
 #endif
+constexpr int kProfSlots = 16;
+#ifndef PFB_SMOOTH_SPLIT
+#define PFB_SMOOTH_SPLIT 1  // 1: half of the deferred smoother job per exchange wait; 0: all of it behind exchange 1
+#endif
 
 struct DeviceProblem {
   int N, T, L, P;
@@ -37,6 +45,7 @@ struct DeviceProblem {
   int G;         // CTAs per filter group
   int n_groups;  // groups resident in this launch
   int per_cta;   // parents owned by one CTA
+  int tile_cap;  // shared-memory CDF tile capacity (entries, multiple of the sub-chunk size)
   int RX, RA, RW;  // ring depths: particles, ancestors, log-weights
   int do_smoother, gen_init, resampling, svl_obs_model;
   int inject, inject_per_filter, obs_per_filter, ws_per_filter;
@@ -50,11 +59,11 @@ struct DeviceProblem {
   const double* inj_u;
   const double* inj_z;
   const double* inj_u_final;
-  void* x_ring;    // [n_ws][RX][N] Real
-  void* logw;      // [n_ws][RW][N] Real
-  int* anc_ring;   // [n_ws][RA][N]
+  void* x_ring;    // [n_ws][RX][NS] Real
+  void* logw;      // [n_ws][RW][NS] Real
+  int* anc_ring;   // [n_ws][RA][NS]
   double* xval;    // [n_groups][2][G]
-  unsigned* xflag; // [n_groups][2][G]
+  unsigned* xcount;  // [n_groups] arrival counters (padded to 32 words each)
   int* abort_flag;
   double* stat_m;     // [B][T+1]
   double* stat_S;     // [B][T+1]
@@ -62,28 +71,22 @@ struct DeviceProblem {
   double* smo_part;   // [B][T+1][G][P+1]
   int* traj_k;        // [B]
   int* traj_idx;      // [B]
-  long long* prof;    // [grid][8] per-phase cycle counters (PFB_PROFILE builds only)
-};
-
-template <int BLOCK, int ITEMS>
-struct Cfg {
-  static constexpr int kBlock = BLOCK;
-  static constexpr int kItems = ITEMS;           // odd: the blocked smem pass is bank-conflict free
-  static constexpr int kChunk = BLOCK * ITEMS;   // parents per shared-memory CDF tile
-  static constexpr int kWarps = BLOCK / 32;
+  long long* prof;    // [grid][kProfSlots] per-phase cycle counters (PFB_PROFILE builds only)
 };
 
 // ---------------------------------------------------------------------------------------------
 template <int MODEL, typename Real, int BLOCK, int ITEMS>
 struct PfKernel {
-  using C = Cfg<BLOCK, ITEMS>;
   using Ops = ModelOps<MODEL, Real>;
+  static constexpr int kChunk = BLOCK * ITEMS;  // parents per scan sub-chunk (ITEMS odd: the
+                                                // thread-blocked smem pass is bank-conflict free)
+  static constexpr int kWarps = BLOCK / 32;
   static constexpr int kRedK = kMaxParams + 2;
 
   const DeviceProblem& p;
-  double* sh_s;    // [kChunk] CDF tile
+  double* sh_s;    // [tile_cap] CDF tile
   double* sh_x;    // [G] exchange staging
-  double* sh_red;  // [kWarps][kRedK]
+  double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
   const int tid, lane, warp, g, q;
   const bool pow2N;
@@ -91,94 +94,110 @@ struct PfKernel {
   unsigned epoch;
   bool aborted;
 #ifdef PFB_PROFILE
-  long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_acc[kProfSlots] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = 0;
 #endif
 
   __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst)
-      : p(prob), sh_s(smem), sh_x(smem + C::kChunk), sh_red(red), sh_c(cst), tid(threadIdx.x),
+      : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g(blockIdx.x % prob.G),
         q(blockIdx.x / prob.G), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
         epoch(0), aborted(false) {}
 
-  // ---- inter-CTA exchange: every CTA of the group contributes one double; on return
-  //      sh_x[0..G) holds all contributions (same bits in every CTA).
-  __device__ void exchange(double v) {
+  // ---- inter-CTA exchange (all-gather of one double per CTA + group barrier).  Arrival is a
+  //      release-increment of one counter per group; ONE thread per CTA polls it (G pollers on one
+  //      L2 line instead of G*G flag reads), then the block reads the G values.  Values are double
+  //      buffered by epoch parity: a CTA can be at most one exchange ahead of the slowest.
+  __device__ void exchange_arrive(double v) {
     const int G = p.G;
     if (G == 1) {
       __syncthreads();
       if (tid == 0) sh_x[0] = v;
-      __syncthreads();
       return;
     }
     ++epoch;
     double* val = p.xval + ((size_t)q * 2 + (epoch & 1u)) * G;
-    unsigned* flg = p.xflag + ((size_t)q * 2 + (epoch & 1u)) * G;
+    unsigned* cnt = p.xcount + (size_t)q * 32;
     __syncthreads();  // all global writes of this CTA precede the release below
     if (tid == 0) {
       val[g] = v;
-      __threadfence();
-      st_release_u32(flg + g, epoch);
+      red_release_add_u32(cnt, 1u);
     }
-    for (int i = tid; i < G; i += BLOCK) {
+  }
+
+  // second half: waits until every CTA of the group has arrived; sh_x[0..G) then holds all values.
+  // Independent work placed between arrive and wait overlaps the exchange latency and the skew.
+  __device__ void exchange_wait() {
+    const int G = p.G;
+    if (G == 1) {
+      __syncthreads();
+      return;
+    }
+    const double* val = p.xval + ((size_t)q * 2 + (epoch & 1u)) * G;
+    const unsigned* cnt = p.xcount + (size_t)q * 32;
+    int ab = 0;
+    if (tid == 0) {
+      const unsigned target = epoch * (unsigned)G;
       long long spins = 0;
-      while ((int)(ld_acquire_u32(flg + i) - epoch) < 0) {
-        if (++spins > p.spin_limit || ld_relaxed_i32(p.abort_flag) != 0) {
+      while ((int)(ld_acquire_u32(cnt) - target) < 0) {
+        if ((++spins & 1023) == 0 && (spins > p.spin_limit || ld_relaxed_i32(p.abort_flag) != 0)) {
           atomicExch(p.abort_flag, 1);
-          aborted = true;
+          ab = 1;
           break;
         }
       }
-      sh_x[i] = ld_cg(val + i);
     }
-    aborted = __syncthreads_or(aborted ? 1 : 0) != 0;  // block-uniform
+    aborted = __syncthreads_or(ab) != 0;  // block-uniform; orders the reads below after the acquire
+    for (int i = tid; i < G; i += BLOCK) sh_x[i] = ld_cg(val + i);
+    __syncthreads();
+  }
+
+  __device__ void exchange(double v) {
+    exchange_arrive(v);
+    exchange_wait();
   }
 
   __device__ double xchg_max() {  // order independent
     double m = -INFINITY;
-    for (int i = tid; i < p.G; i += BLOCK) m = fmax(m, sh_x[i]);
+    for (int i = tid; i < p.G; i += BLOCK) m = dmax(m, sh_x[i]);
     return block_max(m);
   }
 
   // Prefix sums of sh_x in a fixed order.  incl(i) = offset of the lane segment holding i (a
   // shuffle scan of the segment totals) + the running sum inside the segment; every CTA evaluates
   // the same function on the same array, so neighbouring CTAs agree bit for bit on their common
-  // boundary: excl(g) := incl(g-1).
-  __device__ void xchg_prefix(double& excl, double& incl, double& total) {
+  // boundary: excl(g) := incl(g-1).  Results land in sh_red[0..2] = (excl, incl, total); the caller
+  // synchronises.
+  __device__ void xchg_prefix_warp0() {
     const int G = p.G;
-    if (warp == 0) {
-      const int W = (G + 31) / 32;
-      const int b0 = lane * W;
-      double run = 0.0;
-      for (int k = 0; k < W; ++k) {
-        const int i = b0 + k;
-        if (i < G) run += sh_x[i];
-      }
-      const double lane_incl = warp_inclusive_scan(run, lane);
-      double r = __shfl_up_sync(0xffffffffu, lane_incl, 1);
-      if (lane == 0) r = 0.0;
-      double vp = 0.0, vc = 0.0, vt = 0.0;
-      bool hp = false, hc = false, ht = false;
-      for (int k = 0; k < W; ++k) {
-        const int i = b0 + k;
-        if (i < G) {
-          r += sh_x[i];
-          if (i == g - 1) { vp = r; hp = true; }
-          if (i == g) { vc = r; hc = true; }
-          if (i == G - 1) { vt = r; ht = true; }
-        }
-      }
-      const unsigned wp = __ballot_sync(0xffffffffu, hp);
-      const unsigned wc = __ballot_sync(0xffffffffu, hc);
-      const unsigned wt = __ballot_sync(0xffffffffu, ht);
-      vp = wp ? __shfl_sync(0xffffffffu, vp, __ffs(wp) - 1) : 0.0;
-      vc = __shfl_sync(0xffffffffu, vc, __ffs(wc) - 1);
-      vt = __shfl_sync(0xffffffffu, vt, __ffs(wt) - 1);
-      if (lane == 0) { sh_red[0] = vp; sh_red[1] = vc; sh_red[2] = vt; }
+    const int W = (G + 31) / 32;
+    const int b0 = lane * W;
+    double run = 0.0;
+    for (int k = 0; k < W; ++k) {
+      const int i = b0 + k;
+      if (i < G) run += sh_x[i];
     }
-    __syncthreads();
-    excl = sh_red[0]; incl = sh_red[1]; total = sh_red[2];
-    __syncthreads();
+    const double lane_incl = warp_inclusive_scan(run, lane);
+    double r = __shfl_up_sync(0xffffffffu, lane_incl, 1);
+    if (lane == 0) r = 0.0;
+    double vp = 0.0, vc = 0.0, vt = 0.0;
+    bool hp = false, hc = false, ht = false;
+    for (int k = 0; k < W; ++k) {
+      const int i = b0 + k;
+      if (i < G) {
+        r += sh_x[i];
+        if (i == g - 1) { vp = r; hp = true; }
+        if (i == g) { vc = r; hc = true; }
+        if (i == G - 1) { vt = r; ht = true; }
+      }
+    }
+    const unsigned wp = __ballot_sync(0xffffffffu, hp);
+    const unsigned wc = __ballot_sync(0xffffffffu, hc);
+    const unsigned wt = __ballot_sync(0xffffffffu, ht);
+    vp = wp ? __shfl_sync(0xffffffffu, vp, __ffs(wp) - 1) : 0.0;
+    vc = __shfl_sync(0xffffffffu, vc, __ffs(wc) - 1);
+    vt = __shfl_sync(0xffffffffu, vt, __ffs(wt) - 1);
+    if (lane == 0) { sh_red[0] = vp; sh_red[1] = vc; sh_red[2] = vt; }
   }
 
   __device__ double block_max(double v) {
@@ -186,19 +205,14 @@ struct PfKernel {
     __syncthreads();
     if (lane == 0) sh_red[warp] = v;
     __syncthreads();
-    double r = -INFINITY;
-    if (warp == 0) {
-      for (int i = lane; i < C::kWarps; i += 32) r = fmax(r, sh_red[i]);
-      r = warp_max(r);
-      if (lane == 0) sh_red[0] = r;
-    }
-    __syncthreads();
-    r = sh_red[0];
+    double r = (lane < kWarps) ? sh_red[lane] : -INFINITY;  // every warp reduces the same values
+    r = warp_max(r);
     __syncthreads();
     return r;
   }
 
-  // sums K accumulators over the block; result valid in thread 0 (fixed tree)
+  // sums K accumulators over the block; result valid in thread 0 (fixed tree): warp shuffles, then
+  // warp k reduces accumulator k across the warps.
   template <int K>
   __device__ void block_sum(double (&v)[K]) {
 #pragma unroll
@@ -206,16 +220,18 @@ struct PfKernel {
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) sh_red[warp * kRedK + k] = v[k];
+      for (int k = 0; k < K; ++k) sh_red[k * 32 + warp] = v[k];
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp < K) {
+      double r = (lane < kWarps) ? sh_red[warp * 32 + lane] : 0.0;
+      r = warp_sum(r);
+      if (lane == 0) sh_red[8 * 32 + warp] = r;
+    }
+    __syncthreads();
+    if (tid == 0) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        double r = 0.0;
-        for (int i = lane; i < C::kWarps; i += 32) r += sh_red[i * kRedK + k];
-        v[k] = warp_sum(r);
-      }
+      for (int k = 0; k < K; ++k) v[k] = sh_red[8 * 32 + k];
     }
     __syncthreads();
   }
@@ -229,7 +245,7 @@ struct PfKernel {
     __syncthreads();
     int r = 0;
     if (warp == 0) {
-      for (int i = lane; i < C::kWarps; i += 32) r += red[i];
+      for (int i = lane; i < kWarps; i += 32) r += red[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     }
@@ -237,103 +253,142 @@ struct PfKernel {
     return r;  // valid in warp 0
   }
 
-  // ---- tile load: sh_s[jl] = exp(logw[j] - m) for the chunk [c0, c0+len); optional sum s*x
-  __device__ void load_chunk(const Real* lw, const Real* xg, int c0, int len, double m, double* accF) {
+  // ---- tile load: tile[jl] = exp(logw[j] - m) for the sub-chunk [c0, c0+len); optional sum s*x
+  __device__ void load_chunk(double* tile, const Real* lw, const Real* xg, int c0, int len, double m,
+                             double* accF) {
+    Real l[ITEMS], xv[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int jl = k * BLOCK + tid;
+      l[k] = (jl < len) ? ld_cg(lw + c0 + jl) : (Real)(-INFINITY);
+      if (accF) xv[k] = (jl < len) ? ld_cg(xg + c0 + jl) : (Real)0;
+    }
     double f = 0.0;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
       const int jl = k * BLOCK + tid;
-      double s = 0.0;
-      if (jl < len) {
-        s = shifted_weight<Real>(ld_cg(lw + c0 + jl), m);
-        if (accF) f += s * (double)ld_cg(xg + c0 + jl);
-      }
-      sh_s[jl] = s;
+      const double s = (jl < len) ? shifted_weight<Real>(l[k], m) : 0.0;
+      if (accF) f += s * (double)xv[k];
+      tile[jl] = s;
     }
     if (accF) *accF += f;
     __syncthreads();
   }
 
-  // ---- in-place inclusive scan of sh_s[0..kChunk): thread-blocked runs (odd ITEMS: no bank
-  //      conflicts), warp shuffle scan of run totals, warp totals through shared memory.
-  __device__ double scan_chunk() {
-    double v[ITEMS];
+  // ---- in-place inclusive scan of tile[0..kChunk): thread-blocked runs, warp shuffle scan of the
+  //      run totals, warp totals through shared memory.  Returns the sub-chunk total.
+  __device__ double scan_chunk(double* tile) {
     double run = 0.0;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      run += sh_s[tid * ITEMS + k];
-      v[k] = run;
-    }
+    for (int k = 0; k < ITEMS; ++k) run += tile[tid * ITEMS + k];
     const double incl = warp_inclusive_scan(run, lane);
     if (lane == 31) sh_red[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-      double w = (lane < C::kWarps) ? sh_red[lane] : 0.0;
-      const double wi = warp_inclusive_scan(w, lane);
-      sh_red[lane] = wi - w;  // exclusive offsets of the warps (kWarps <= 32)
-      if (lane == 31) sh_red[32] = wi;
-    }
-    __syncthreads();
-    const double off = sh_red[warp] + (incl - run);
-    const double total = sh_red[32];
+    double w = (lane < kWarps) ? sh_red[lane] : 0.0;  // every warp scans the warp totals itself
+    const double wi = warp_inclusive_scan(w, lane);
+    const double woff = __shfl_sync(0xffffffffu, wi - w, warp);
+    const double total = __shfl_sync(0xffffffffu, wi, 31);
+    double r = woff + (incl - run);
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) sh_s[tid * ITEMS + k] = off + v[k];
+    for (int k = 0; k < ITEMS; ++k) {
+      r += tile[tid * ITEMS + k];
+      tile[tid * ITEMS + k] = r;
+    }
     __syncthreads();
     return total;
   }
 
   // ---- fixed-lag smoother increment for smoothing time i with weights of generation tau
-  //      (standard.py:146-169); s[j] is read from the (unscanned) tile in sh_s.
-  __device__ void smooth_chunk(const Real* xr, const int* ar, const double* obs, int tau, int i,
-                               int c0, int len, double (&acc)[kMaxParams + 1]) {
+  //      (standard.py:146-169).  The weights s[j] = exp(logw_tau[j] - m_tau) are recomputed from
+  //      the log-weight ring, so the job only reads data that is final and can run while the CTA
+  //      waits for an exchange.
+  template <int NI>
+  __device__ void smooth_chunk(const Real* lw, double m_tau, const Real* xr, const int* ar,
+                               const double* obs, int tau, int i, int c0, int len,
+                               double (&acc)[kMaxParams + 1]) {
     const size_t NS = (size_t)p.NS;
-    int cur[ITEMS], nxt[ITEMS];
+    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+    int cur[NI], nxt[NI];
+    Real l[NI];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
+    for (int k = 0; k < NI; ++k) {
       const int jl = k * BLOCK + tid;
       cur[k] = (jl < len) ? c0 + jl : c0;
       nxt[k] = cur[k];
+      l[k] = (jl < len) ? ld_hint(lw + c0 + jl, once) : (Real)(-INFINITY);
     }
-    int slot = tau % p.RA;
+    const int* a = ar + (size_t)(tau % p.RA) * NS;
+    const int* a_wrap = ar + (size_t)(p.RA - 1) * NS;
     for (int lvl = tau; lvl > i; --lvl) {
-      const int* a = ar + (size_t)slot * NS;
-      slot = (slot == 0) ? p.RA - 1 : slot - 1;
 #pragma unroll
-      for (int k = 0; k < ITEMS; ++k) {
+      for (int k = 0; k < NI; ++k) {
         nxt[k] = cur[k];
-        cur[k] = ld_cg(a + cur[k]);
+        cur[k] = ld_hint(a + cur[k], keep);
       }
+      a = (a == ar) ? a_wrap : a - NS;
     }
     const Real* xi = xr + (size_t)(i % p.RX) * NS;
     const Real* xn = xr + (size_t)((i + 1) % p.RX) * NS;
     const double y = __ldg(obs + i);
+    Real xc[NI], xnext[NI];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
+    for (int k = 0; k < NI; ++k) {
+      xc[k] = ld_hint(xi + cur[k], once);
+      xnext[k] = ld_hint(xn + nxt[k], once);
+    }
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
       const int jl = k * BLOCK + tid;
-      const double sw = (jl < len) ? sh_s[jl] : 0.0;
-      const Real xc = ld_cg(xi + cur[k]);
-      const Real xnext = ld_cg(xn + nxt[k]);
+      const Real xck = xc[k], xnk = xnext[k];
+      const double sw = (jl < len) ? shifted_weight<Real>(l[k], m_tau) : 0.0;
       double gr[kMaxParams];
-      Ops::gradient(sh_c, xnext, xc, y, gr);
-      const double t0 = (double)xc * sw;
-      if (!isnan(t0)) acc[0] += t0;  // np.nansum
+      Ops::gradient(sh_c, xnk, xck, y, gr);
+      const double t0 = (double)xck * sw;
+      // np.nansum: NaN terms are skipped.  A term can only be NaN when a state is not finite.
+      if (isfinite((double)xck) && isfinite((double)xnk)) {
+        acc[0] += t0;
 #pragma unroll
-      for (int pp = 0; pp < kMaxParams; ++pp) {
-        const double tp = gr[pp] * sw;
-        if (!isnan(tp)) acc[1 + pp] += tp;
+        for (int pp = 0; pp < kMaxParams; ++pp) acc[1 + pp] += gr[pp] * sw;
+      } else {
+        if (!isnan(t0)) acc[0] += t0;
+#pragma unroll
+        for (int pp = 0; pp < kMaxParams; ++pp) {
+          const double tp = gr[pp] * sw;
+          if (!isnan(tp)) acc[1 + pp] += tp;
+        }
       }
+    }
+  }
+
+  // smoother increment of lag time `tau` over the sub-chunks [c_lo, c_hi) of this CTA's range
+  __device__ void smooth_job(const Real* lwr, double m_tau, const Real* xr, const int* ar,
+                             const double* obs, int tau, int j_begin, int j_end, int c_lo, int c_hi,
+                             double (&acc)[kMaxParams + 1]) {
+    const Real* lw = lwr + (size_t)(tau % p.RW) * p.NS;
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int c0 = j_begin + c * kChunk;
+      smooth_chunk<ITEMS>(lw, m_tau, xr, ar, obs, tau, tau - p.L, c0, min(kChunk, j_end - c0), acc);
+    }
+  }
+
+  __device__ void write_smooth_partials(int b, int i, double (&acc)[kMaxParams + 1]) {
+    block_sum(acc);
+    if (tid == 0) {
+      double* dst = p.smo_part + (((size_t)b * (p.T + 1) + i) * p.G + g) * (p.P + 1);
+      for (int k = 0; k <= p.P; ++k) dst[k] = acc[k];
     }
   }
 
   // position of child n on the unit interval (resampling.pyx:72 systematic, :51 stratified)
   __device__ __forceinline__ double position(int n, double u, int t, const double* inj_u_t,
                                              unsigned long long eval_id) const {
+    double a;
     if (p.resampling == 1) {
       u = p.inject ? ld_cg(inj_u_t + n) : philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)n);
-      const double a = __dadd_rn(u, (double)n);
-      return pow2N ? __dmul_rn(a, invN) : __ddiv_rn(a, (double)p.N);
+      a = __dadd_rn(u, (double)n);
+    } else {
+      a = __dadd_rn((double)n, u);
     }
-    const double a = __dadd_rn((double)n, u);
     return pow2N ? __dmul_rn(a, invN) : __ddiv_rn(a, (double)p.N);  // x * 2^-k == x / 2^k exactly
   }
 
@@ -349,89 +404,115 @@ struct PfKernel {
     return n;
   }
 
-  // #{ jl in [lo, len) : sh_s[jl] <= pos } + lo   (upper bound)
-  __device__ __forceinline__ int upper_bound_tile(double pos, int lo, int len) const {
-    int hi = len;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (sh_s[mid] <= pos) lo = mid + 1; else hi = mid;
+  // #{ jl in [0, len) : tile[jl] <= pos }  -- branch-free power-of-two descent; `top` is the
+  // largest power of two <= len; `ta` = shared-window address of tile[-1]
+  __device__ __forceinline__ int upper_bound_tile(uint32_t ta, double pos, int len, int top) const {
+    int lo = 0;
+    for (int step = top; step > 0; step >>= 1) {
+      const int probe = lo + step;
+      if (probe <= len && lds_f64(ta + 8u * probe) <= pos) lo = probe;
     }
     return lo;
   }
 
-  // parent (tile-local) of a child at `pos`, knowing that it is >= lo (children are monotone)
-  __device__ __forceinline__ int next_parent(double pos, int lo, int len) const {
-    if (sh_s[lo] > pos) return lo;
-    if (lo + 1 < len && sh_s[lo + 1] > pos) return lo + 1;
-    return upper_bound_tile(pos, (lo + 2 < len) ? lo + 2 : len, len);
+  // parent (tile-local) of a child at `pos`, knowing that it is >= lo (children are monotone):
+  // branch-free 3-step descent inside the window [lo, lo+8); the full descent only when the
+  // answer lies beyond the window (several consecutive parents without offspring)
+  __device__ __forceinline__ int next_parent(uint32_t ta, double pos, int lo, int len, int top) const {
+    const int wend = min(lo + 8, len);
+    if (lds_f64(ta + 8u * wend) <= pos) {  // not inside the window
+      return (wend == len) ? len : upper_bound_tile(ta, pos, len, top);
+    }
+    int r = lo;
+#pragma unroll
+    for (int step = 4; step > 0; step >>= 1) {
+      const int probe = r + step;
+      if (probe <= wend && lds_f64(ta + 8u * probe) <= pos) r = probe;
+    }
+    return r;
   }
 
-  // ---- children of the CDF tile in sh_s: resample + propagate + weight (phase B).  A thread owns
-  //      4 consecutive children: one binary search, then short forward merges; 32-byte stores.
-  __device__ void children_chunk(const Real* x_prev, Real* x_new, Real* lw_new, int* anc_new,
-                                 const double* inj_z_t, const double* inj_u_t, int t, double u,
-                                 unsigned long long eval_id, double y_prop, double y_obs, int c0,
-                                 int len, int n_lo, int n_hi, double& mx) {
+  // ---- children of the normalised CDF tile: resample + propagate + weight (phase B).  A thread
+  //      owns 4 consecutive children: one binary search, then short forward merges.
+  __device__ void children_chunk(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
+                                 int* anc_new, const double* inj_z_t, const double* inj_u_t, int t,
+                                 double u, unsigned long long eval_id, double y_prop, double y_obs,
+                                 int c0, int len, int n_lo, int n_hi, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
+    int top = 1;
+    while (top * 2 <= len) top *= 2;
+    const uint32_t ta = smem_base(tile) - 8u;  // address of tile[-1]
+    const uint64_t keep = l2_policy_evict_last();
+    double cst[kNumConsts];
+    load_step_consts<MODEL>(smem_base(sh_c), cst);
     for (int qq = q0 + tid; qq < q1; qq += BLOCK) {
       const int nb = 4 * qq;
-      Real z[4];
-      if (p.inject) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int n = nb + e;
-          z[e] = (n >= n_lo && n < n_hi) ? (Real)ld_cg(inj_z_t + n) : (Real)0;
-        }
-      } else {
-        philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq), z[0], z[1]);
-        philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq + 1), z[2], z[3]);
-      }
+      const bool full = nb >= n_lo && nb + 3 < n_hi;
       int j[4];
       int lo = -1;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int n = nb + e;
         j[e] = 0;
-        if (n >= n_lo && n < n_hi) {
+        if (full || (n >= n_lo && n < n_hi)) {
           const double pos = position(n, u, t, inj_u_t, eval_id);
-          lo = (lo < 0) ? upper_bound_tile(pos, 0, len) : next_parent(pos, lo, len);
+          lo = (lo < 0) ? upper_bound_tile(ta, pos, len, top) : next_parent(ta, pos, lo, len, top);
           if (lo > len - 1) lo = len - 1;
           j[e] = lo;
         }
       }
-      Real xv[4], lv[4];
+      PFB_TICK(11);
+      Real xp[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = nb + e;
-        xv[e] = 0; lv[e] = 0;
-        if (n >= n_lo && n < n_hi) {
-          xv[e] = Ops::propagate(sh_c, ld_cg(x_prev + c0 + j[e]), z[e], y_prop);
-          lv[e] = Ops::logweight(sh_c, xv[e], y_obs);
-          mx = fmax(mx, (double)lv[e]);
-        }
-      }
-      if (nb >= n_lo && nb + 3 < n_hi) {
-        if (sizeof(Real) == 8) {
-          double2* xd = reinterpret_cast<double2*>(x_new + nb);
-          double2* ld = reinterpret_cast<double2*>(lw_new + nb);
-          xd[0] = make_double2((double)xv[0], (double)xv[1]);
-          xd[1] = make_double2((double)xv[2], (double)xv[3]);
-          ld[0] = make_double2((double)lv[0], (double)lv[1]);
-          ld[1] = make_double2((double)lv[2], (double)lv[3]);
+      for (int e = 0; e < 4; ++e) xp[e] = ld_cg(x_prev + c0 + j[e]);
+#ifdef PFB_PROFILE
+      if (xp[0] == (Real)123456.789) mx = 0.0;  // force the gathers to complete here
+      PFB_TICK(12);
+#endif
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
+        Real z0, z1;
+        if (p.inject) {
+          const int n = nb + 2 * h;
+          z0 = (n >= n_lo && n < n_hi) ? (Real)ld_cg(inj_z_t + n) : (Real)0;
+          z1 = (n + 1 >= n_lo && n + 1 < n_hi) ? (Real)ld_cg(inj_z_t + n + 1) : (Real)0;
         } else {
-          *reinterpret_cast<float4*>(x_new + nb) = make_float4((float)xv[0], (float)xv[1], (float)xv[2], (float)xv[3]);
-          *reinterpret_cast<float4*>(lw_new + nb) = make_float4((float)lv[0], (float)lv[1], (float)lv[2], (float)lv[3]);
+          philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq + h), z0, z1);
         }
-        *reinterpret_cast<int4*>(anc_new + nb) = make_int4(c0 + j[0], c0 + j[1], c0 + j[2], c0 + j[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int n = nb + e;
-          if (n >= n_lo && n < n_hi) { x_new[n] = xv[e]; lw_new[n] = lv[e]; anc_new[n] = c0 + j[e]; }
+#ifdef PFB_PROFILE
+        if (z0 == (Real)123456.789) mx = 0.0;
+        PFB_TICK(13);
+#endif
+        const Real xa = Ops::propagate(cst, xp[2 * h], z0, y_prop);
+        const Real xb = Ops::propagate(cst, xp[2 * h + 1], z1, y_prop);
+        const Real la = Ops::logweight(cst, xa, y_obs);
+        const Real lb = Ops::logweight(cst, xb, y_obs);
+        const int n = nb + 2 * h;
+#ifdef PFB_PROFILE
+        if (la == (Real)123456.789) mx = 0.0;
+        PFB_TICK(14);
+#endif
+        if (full) {
+          mx = dmax(mx, dmax((double)la, (double)lb));
+          store2(x_new + n, xa, xb);
+          store2(lw_new + n, la, lb);
+          st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
+        } else {
+          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
         }
+        PFB_TICK(15);
       }
     }
   }
+
+  static __device__ __forceinline__ void store2(double* dst, double a, double b) {
+    *reinterpret_cast<double2*>(dst) = make_double2(a, b);
+  }
+  static __device__ __forceinline__ void store2(float* dst, float a, float b) {
+    *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+  }
+  static __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }
 
   // ---- one filter evaluation (all T steps) -------------------------------------------------
   __device__ void run_filter(int b) {
@@ -455,7 +536,9 @@ struct PfKernel {
 
     const int j_begin = min(g * p.per_cta, N);
     const int j_end = min(j_begin + p.per_cta, N);
-    const int n_chunks = (j_end - j_begin + C::kChunk - 1) / C::kChunk;
+    const int own = j_end - j_begin;
+    const int n_chunks = (own + kChunk - 1) / kChunk;
+    const bool resident = n_chunks * kChunk <= p.tile_cap;  // the whole tile stays in shared memory
     const bool last_cta = (j_end == N);
 
     // ---- generation 0 (standard.py:62-67): stationary draw or fixed value, uniform weights
@@ -475,6 +558,7 @@ struct PfKernel {
     }
     exchange(0.0);
     double m = xchg_max();
+    double m_prev = m;  // max log-weight of generation tau-1 (for the deferred smoother job)
 
     for (int t = 1; t <= T + 1; ++t) {
       if (aborted) return;
@@ -482,80 +566,17 @@ struct PfKernel {
       const Real* x_prev = xr + (size_t)(tau % p.RX) * NS;
       const Real* lw_prev = lwr + (size_t)(tau % p.RW) * NS;
       const bool final_step = (t == T + 1);
-      const int i_sm = (p.do_smoother && !final_step && tau >= L) ? tau - L : -1;
-
-#ifdef PFB_PROFILE
-      prof_t = clock64();
-#endif
-      // ---------------- phase A
-      double accF = 0.0, A = 0.0, chunk_total = 0.0;
+      // Deferred smoother job of this step: lag time tau-1 (its weights, ancestors and states are
+      // final), split over the two exchange waits.  Lag time T is handled by the tail below.
+      const int tau_sm = tau - 1;
+      const bool job = p.do_smoother && tau_sm >= L;
+      const int c_half = PFB_SMOOTH_SPLIT ? (n_chunks + 1) / 2 : n_chunks;
       double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int c = 0; c < n_chunks; ++c) {
-        const int c0 = j_begin + c * C::kChunk;
-        const int len = min(C::kChunk, j_end - c0);
-        load_chunk(lw_prev, x_prev, c0, len, m, &accF);
-        PFB_TICK(8);
-        if (i_sm >= 0) {
-          smooth_chunk(xr, ar, obs, tau, i_sm, c0, len, acc);
-          __syncthreads();
-        }
-        PFB_TICK(9);
-        chunk_total = scan_chunk();
-        A += chunk_total;
-      }
-      PFB_TICK(0);
-      {
-        double red[kMaxParams + 2] = {accF, acc[0], acc[1], acc[2], acc[3], acc[4]};
-        block_sum(red);
-        if (tid == 0) {
-          p.filt_part[((size_t)b * (T + 1) + tau) * G + g] = red[0];
-          if (i_sm >= 0) {
-            double* dst = p.smo_part + (((size_t)b * (T + 1) + i_sm) * G + g) * (P + 1);
-            for (int k = 0; k <= P; ++k) dst[k] = red[1 + k];
-          }
-        }
-      }
-      PFB_TICK(1);
-      exchange(A);
-      PFB_TICK(2);
-      double Pg, Pg1, S;
-      xchg_prefix(Pg, Pg1, S);
-      if (g == 0 && tid == 0) {
-        p.stat_m[(size_t)b * (T + 1) + tau] = m;
-        p.stat_S[(size_t)b * (T + 1) + tau] = S;
-      }
 
-      // ---------------- smoother tail (standard.py:146: lag = T for the last L times)
-      if (final_step && p.do_smoother) {
-        const int i_first = (T - L > 0) ? T - L : 0;
-        for (int i = T - 1; i >= i_first; --i) {
-          double ta[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
-          for (int c = 0; c < n_chunks; ++c) {
-            const int c0 = j_begin + c * C::kChunk;
-            const int len = min(C::kChunk, j_end - c0);
-            __syncthreads();
-            load_chunk(lw_prev, x_prev, c0, len, m, nullptr);
-            smooth_chunk(xr, ar, obs, tau, i, c0, len, ta);
-          }
-          block_sum(ta);
-          if (tid == 0) {
-            double* dst = p.smo_part + (((size_t)b * (T + 1) + i) * G + g) * (P + 1);
-            for (int k = 0; k <= P; ++k) dst[k] = ta[k];
-          }
-        }
-        // restore the scanned tile of the (single) chunk for the trajectory draw below
-        if (n_chunks == 1) {
-          __syncthreads();
-          load_chunk(lw_prev, x_prev, j_begin, j_end - j_begin, m, nullptr);
-          chunk_total = scan_chunk();
-        }
-      }
-
-      // ---------------- phase B
+      // per-step scalars, issued early so that their latency hides behind phase A
       double u = 0.0, y_prop = 0.0, y_obs = 0.0;
       const double* inj_u_t = nullptr;
       const double* inj_z_t = nullptr;
-      Real* x_new = nullptr; Real* lw_new = nullptr; int* anc_new = nullptr;
       if (!final_step) {
         if (p.inject) {
           inj_u_t = inj_u + (size_t)t * u_row;
@@ -566,53 +587,138 @@ struct PfKernel {
         }
         y_obs = __ldg(obs + t);
         y_prop = p.svl_obs_model ? __ldg(obs + t - 1) : y_obs;  // Q10
-        x_new = xr + (size_t)(t % p.RX) * NS;
-        lw_new = lwr + (size_t)(t % p.RW) * NS;
-        anc_new = ar + (size_t)(t % p.RA) * NS;
       } else {
         u = p.inject ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
       }
-      const double invS = 1.0 / S;  // the CDF is (prefix sum) * (1/S) everywhere, boundaries included
-      const int n_begin = final_step ? 0 : ((g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg, invS), u, t, inj_u_t, eval_id));
-      const int n_end = final_step ? 0 : (last_cta ? N : lower_bound_child(__dmul_rn(Pg1, invS), u, t, inj_u_t, eval_id));
+
+#ifdef PFB_PROFILE
+      prof_t = clock64();
+#endif
+      // ---------------- phase A
+      double accF = 0.0, A = 0.0, chunk_total = 0.0;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = j_begin + c * kChunk;
+        const int len = min(kChunk, j_end - c0);
+        double* tile = sh_s + (resident ? c * kChunk : 0);
+        load_chunk(tile, lw_prev, x_prev, c0, len, m, &accF);
+        PFB_TICK(8);
+        chunk_total = scan_chunk(tile);
+        if (resident && tid == 0) sh_red[264 + c] = chunk_total;  // sub-chunk totals for phase B
+        A += chunk_total;
+      }
+      PFB_TICK(0);
+      {
+        double red[1] = {accF};
+        block_sum(red);
+        if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * G + g] = red[0];
+      }
+      PFB_TICK(1);
+      exchange_arrive(A);
+      if (job) smooth_job(lwr, m_prev, xr, ar, obs, tau_sm, j_begin, j_end, 0, final_step ? n_chunks : c_half, acc);
+      PFB_TICK(9);
+      exchange_wait();
+      PFB_TICK(2);
+      // prefix over the group + this CTA's children range; lanes 0 / 1 of warp 0 evaluate the two
+      // boundaries side by side
+      if (warp == 0) {
+        xchg_prefix_warp0();
+        __syncwarp();
+        const double Pg_ = sh_red[0], Pg1_ = sh_red[1], S_ = sh_red[2];
+        const double invS_ = 1.0 / S_;  // the CDF is (prefix sum) * (1/S) everywhere
+        if (!final_step && lane < 2) {
+          int nb;
+          if (lane == 0) nb = (g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg_, invS_), u, t, inj_u_t, eval_id);
+          else nb = last_cta ? N : lower_bound_child(__dmul_rn(Pg1_, invS_), u, t, inj_u_t, eval_id);
+          reinterpret_cast<int*>(sh_red + 4)[lane] = nb;
+        }
+        if (lane == 0) sh_red[3] = invS_;
+      }
+      __syncthreads();
+      const double Pg = sh_red[0], S = sh_red[2], invS = sh_red[3];
+      const int n_begin = final_step ? 0 : reinterpret_cast<int*>(sh_red + 4)[0];
+      const int n_end = final_step ? 0 : reinterpret_cast<int*>(sh_red + 4)[1];
+      if (g == 0 && tid == 0) {
+        p.stat_m[(size_t)b * (T + 1) + tau] = m;
+        p.stat_S[(size_t)b * (T + 1) + tau] = S;
+      }
+
+      // ---------------- smoother tail (standard.py:146: lag = T for the last L times)
+      if (final_step && p.do_smoother) {
+        if (job) write_smooth_partials(b, tau_sm - L, acc);  // the deferred job of lag time T-1
+        const int i_first = (T - L > 0) ? T - L : 0;
+        for (int i = T - 1; i >= i_first; --i) {
+          double ta[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
+          for (int c = 0; c < n_chunks; ++c) {
+            const int c0 = j_begin + c * kChunk;
+            smooth_chunk<ITEMS>(lw_prev, m, xr, ar, obs, tau, i, c0, min(kChunk, j_end - c0), ta);
+          }
+          write_smooth_partials(b, i, ta);
+        }
+      }
+
+      // ---------------- phase B
+      Real* x_new = xr + (size_t)(t % p.RX) * NS;
+      Real* lw_new = lwr + (size_t)(t % p.RW) * NS;
+      int* anc_new = ar + (size_t)(t % p.RA) * NS;
       PFB_TICK(3);
       double mx = -INFINITY;
-      int n_cursor = n_begin, traj_cnt = 0;
-      double base = Pg;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int c0 = j_begin + c * C::kChunk;
-        const int len = min(C::kChunk, j_end - c0);
-        if (n_chunks > 1) {
-          __syncthreads();
-          load_chunk(lw_prev, x_prev, c0, len, m, nullptr);
-          chunk_total = scan_chunk();
-        }
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-          const int jl = k * BLOCK + tid;
-          if (jl < len) sh_s[jl] = __dmul_rn(__dadd_rn(base, sh_s[jl]), invS);
-        }
-        __syncthreads();
-        PFB_TICK(10);
-        if (final_step) {
-          // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
+      int traj_cnt = 0;
+      if (resident) {
+        // normalise the whole tile: (group prefix + sub-chunk carry + local prefix) * (1/S)
+        double base = Pg;
+        for (int c = 0; c < n_chunks; ++c) {
+          double* tile = sh_s + c * kChunk;
+          const int len = min(kChunk, own - c * kChunk);
 #pragma unroll
           for (int k = 0; k < ITEMS; ++k) {
             const int jl = k * BLOCK + tid;
-            if (jl < len && sh_s[jl] <= u) ++traj_cnt;
+            if (jl < len) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
           }
-        } else {
-          const double next_base = base + chunk_total;
-          int n_hi = n_end;
-          if (c + 1 < n_chunks) {
-            n_hi = lower_bound_child(__dmul_rn(next_base, invS), u, t, inj_u_t, eval_id);
-            n_hi = max(n_cursor, min(n_hi, n_end));
-          }
-          children_chunk(x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
-                         y_obs, c0, len, n_cursor, n_hi, mx);
-          n_cursor = n_hi;
+          base += sh_red[264 + c];
         }
-        base += chunk_total;
+        __syncthreads();
+        if (final_step) {
+          // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
+          for (int jl = tid; jl < own; jl += BLOCK)
+            if (sh_s[jl] <= u) ++traj_cnt;
+        } else {
+          children_chunk(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
+                         y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
+        }
+      } else {
+        int n_cursor = n_begin;
+        double base = Pg;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int c0 = j_begin + c * kChunk;
+          const int len = min(kChunk, j_end - c0);
+          __syncthreads();
+          load_chunk(sh_s, lw_prev, x_prev, c0, len, m, nullptr);
+          chunk_total = scan_chunk(sh_s);
+#pragma unroll
+          for (int k = 0; k < ITEMS; ++k) {
+            const int jl = k * BLOCK + tid;
+            if (jl < len) sh_s[jl] = __dmul_rn(__dadd_rn(base, sh_s[jl]), invS);
+          }
+          __syncthreads();
+          if (final_step) {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+              const int jl = k * BLOCK + tid;
+              if (jl < len && sh_s[jl] <= u) ++traj_cnt;
+            }
+          } else {
+            const double next_base = base + chunk_total;
+            int n_hi = n_end;
+            if (c + 1 < n_chunks) {
+              n_hi = lower_bound_child(__dmul_rn(next_base, invS), u, t, inj_u_t, eval_id);
+              n_hi = max(n_cursor, min(n_hi, n_end));
+            }
+            children_chunk(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
+                           y_prop, y_obs, c0, len, n_cursor, n_hi, mx);
+            n_cursor = n_hi;
+          }
+          base += chunk_total;
+        }
       }
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);
@@ -627,8 +733,15 @@ struct PfKernel {
         PFB_TICK(4);
         mx = block_max(mx);
         PFB_TICK(5);
-        exchange(mx);
+        exchange_arrive(mx);
+        if (job) {
+          smooth_job(lwr, m_prev, xr, ar, obs, tau_sm, j_begin, j_end, c_half, n_chunks, acc);
+          write_smooth_partials(b, tau_sm - L, acc);
+        }
+        PFB_TICK(10);
+        exchange_wait();
         PFB_TICK(6);
+        m_prev = m;
         m = xchg_max();
         PFB_TICK(7);
       }
@@ -639,7 +752,7 @@ struct PfKernel {
 template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const DeviceProblem prob) {
   extern __shared__ double pf_smem[];
-  __shared__ double sh_red[(BLOCK / 32) * (kMaxParams + 2) + 40];
+  __shared__ double sh_red[9 * 32 + 8];
   __shared__ double sh_c[kNumConsts];
   PfKernel<MODEL, Real, BLOCK, ITEMS> k(prob, pf_smem, sh_red, sh_c);
   for (int b = k.q; b < prob.B; b += prob.n_groups) {
@@ -648,7 +761,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const Device
   }
 #ifdef PFB_PROFILE
   if (threadIdx.x == 0)
-    for (int i = 0; i < 12; ++i) prob.prof[(size_t)blockIdx.x * 12 + i] = k.prof_acc[i];
+    for (int i = 0; i < kProfSlots; ++i) prob.prof[(size_t)blockIdx.x * kProfSlots + i] = k.prof_acc[i];
 #endif
 }
 

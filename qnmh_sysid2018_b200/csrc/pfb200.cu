@@ -139,6 +139,8 @@ struct pfb200_handle {
   long long opt_ctas_per_filter = 0;
   long long opt_max_groups = 0;
   long long opt_spin_limit = 20000000LL;
+  long long opt_l2_persist = 0;   // pin the ancestor ring in L2 (access policy window)
+  size_t l2_persist_max = 0, l2_window_max = 0;
   // configured problem
   bool configured = false;
   bool executed = false;
@@ -149,7 +151,7 @@ struct pfb200_handle {
   int n_ws = 0;
   // device buffers
   DevBuf obs, consts, evals, inj_z0, inj_u, inj_z, inj_uf;
-  DevBuf x_ring, logw, anc, xval, xflag, abortf;
+  DevBuf x_ring, logw, anc, xval, xcount, abortf;
   DevBuf stat_m, stat_S, filt_part, smo_part, traj_k, traj_idx;
   DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch, prof;
   std::vector<double> h_consts;
@@ -196,6 +198,8 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
+  h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CUDA_TRY(cudaEventCreate(&h->ev0));
@@ -211,7 +215,7 @@ int pfb200_destroy(pfb200_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->obs, &h->consts, &h->evals, &h->inj_z0, &h->inj_u, &h->inj_z, &h->inj_uf, &h->x_ring,
-                    &h->logw, &h->anc, &h->xval, &h->xflag, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
+                    &h->logw, &h->anc, &h->xval, &h->xcount, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
                     &h->smo_part, &h->traj_k, &h->traj_idx, &h->ll_terms, &h->log_like, &h->filt, &h->smo,
                     &h->grad, &h->traj, &h->scratch, &h->prof};
   for (DevBuf* b : bufs) b->release();
@@ -235,6 +239,7 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
   if (!strcmp(name, "ctas_per_filter")) h->opt_ctas_per_filter = value;
   else if (!strcmp(name, "max_groups")) h->opt_max_groups = value;
   else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
+  else if (!strcmp(name, "l2_persist")) h->opt_l2_persist = value;
   else return fail(PFB200_EINVAL, "pfb200_set_option: unknown option '%s'", name);
   h->configured = false;
   return PFB200_OK;
@@ -248,6 +253,9 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "per_cta")) *value = h->prob.per_cta;
   else if (!strcmp(name, "block_threads")) *value = kBlock;
   else if (!strcmp(name, "chunk")) *value = kChunk;
+  else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
+  else if (!strcmp(name, "l2_persist_max")) *value = (long long)h->l2_persist_max;
+  else if (!strcmp(name, "l2_window_max")) *value = (long long)h->l2_window_max;
   else if (!strcmp(name, "blocks_per_sm")) *value = h->blocks_per_sm;
   else if (!strcmp(name, "cooperative")) *value = h->cooperative ? 1 : 0;
   else if (!strcmp(name, "smem_bytes")) *value = (long long)h->smem_bytes;
@@ -301,27 +309,35 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   // ---- launch geometry
   const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
-  int bps = 0;
-  const size_t smem_max = (size_t)(kChunk + 1024) * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem_max));
-  if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM");
-  h->blocks_per_sm = bps;
-  const int capacity = bps * h->num_sms;
-  int G;
-  if (h->opt_ctas_per_filter > 0) {
-    G = (int)h->opt_ctas_per_filter;
-  } else if (B == 1) {
-    G = (N + kBlock - 1) / kBlock;
-  } else {
-    G = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
+  const size_t smem_limit = 200 * 1024;  // dynamic shared memory we are willing to use per CTA
+  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+  int G = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0;
+  size_t smem = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    // shared memory of the current guess -> co-resident CTAs -> group size
+    smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
+    if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
+    capacity = bps * h->num_sms;
+    if (h->opt_ctas_per_filter > 0) G = (int)h->opt_ctas_per_filter;
+    else if (B == 1) G = (N + kBlock - 1) / kBlock;
+    else G = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
+    if (G > capacity) G = capacity;
+    if (G > 1024) G = 1024;
+    if (G < 1) G = 1;
+    per = (N + G - 1) / G;
+    G = (N + per - 1) / per;  // no empty CTAs
+    const int n_chunks = (per + kChunk - 1) / kChunk;
+    const size_t want = (size_t)n_chunks * kChunk;
+    tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : kChunk;
   }
-  if (G > capacity) G = capacity;
-  if (G > 1024) G = 1024;
-  if (G < 1) G = 1;
-  int per = (N + G - 1) / G;
-  G = (N + per - 1) / per;  // no empty CTAs
-  int n_groups;
+  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
+  if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
+  capacity = bps * h->num_sms;
+  if (G > capacity)
+    return fail(PFB200_ECUDA, "pfb200_configure: %d cooperating CTAs exceed the %d co-resident CTAs", G, capacity);
+  h->blocks_per_sm = bps;
   if (history) {
     n_groups = B;
     if (G > 1 && (long long)B * G > capacity)
@@ -333,15 +349,15 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     if (n_groups < 1) n_groups = 1;
   }
   h->cooperative = G > 1;
-  h->smem_bytes = (size_t)(kChunk + G) * sizeof(double);
+  h->smem_bytes = smem;
   h->n_ws = history ? B : n_groups;
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per;
-  p.RX = history ? T + 1 : L + 2;
-  p.RA = history ? T + 1 : L + 1;
-  p.RW = history ? T + 1 : 2;
+  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
+  p.RX = history ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
+  p.RA = history ? T + 1 : L + 2;
+  p.RW = history ? T + 1 : 3;
   p.do_smoother = do_smoother ? 1 : 0;
   p.gen_init = generate_initial_state ? 1 : 0;
   p.resampling = resampling;
@@ -373,7 +389,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
   CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
-  CUDA_TRY(h->xflag.reserve((size_t)n_groups * 2 * G * 4));
+  CUDA_TRY(h->xcount.reserve((size_t)n_groups * 32 * 4));
   CUDA_TRY(h->abortf.reserve(16));
   CUDA_TRY(h->stat_m.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->stat_S.reserve((size_t)B * T1 * 8));
@@ -387,7 +403,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->smo.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->grad.reserve((size_t)B * P * T1 * 8));
   CUDA_TRY(h->traj.reserve((size_t)B * T1 * 8));
-  CUDA_TRY(h->prof.reserve((size_t)n_groups * G * 12 * 8));
+  CUDA_TRY(h->prof.reserve((size_t)n_groups * G * kProfSlots * 8));
 
   p.obs = h->obs.as<double>();
   p.consts = h->consts.as<double>();
@@ -400,7 +416,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.logw = h->logw.ptr;
   p.anc_ring = h->anc.as<int>();
   p.xval = h->xval.as<double>();
-  p.xflag = h->xflag.as<unsigned>();
+  p.xcount = h->xcount.as<unsigned>();
   p.abort_flag = h->abortf.as<int>();
   p.stat_m = h->stat_m.as<double>();
   p.stat_S = h->stat_S.as<double>();
@@ -437,10 +453,28 @@ int pfb200_execute(pfb200_handle* h) {
   DeviceProblem& p = h->prob;
   const size_t T1 = (size_t)p.T + 1;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->xflag.ptr, 0, (size_t)p.n_groups * 2 * p.G * 4, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, (size_t)p.n_groups * 32 * 4, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
   const dim3 grid(p.n_groups * p.G), block(kBlock);
+  {
+    // The ancestor ring is re-read every time step for L steps (fixed-lag lineage walks) while
+    // particles and log-weights stream through: keep it resident in L2.
+    const size_t anc_bytes = (size_t)h->n_ws * p.RA * p.NS * 4;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (h->opt_l2_persist && p.do_smoother && h->l2_persist_max > 0 && h->l2_window_max > 0) {
+      size_t win = anc_bytes < h->l2_window_max ? anc_bytes : h->l2_window_max;
+      size_t set_aside = win < h->l2_persist_max ? win : h->l2_persist_max;
+      CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+      attr.accessPolicyWindow.base_ptr = h->anc.ptr;
+      attr.accessPolicyWindow.num_bytes = win;
+      attr.accessPolicyWindow.hitRatio = win <= set_aside ? 1.0f : (float)set_aside / (float)win;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    CUDA_TRY(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  }
   CUDA_TRY(cudaEventRecord(h->evk0, h->stream));
   if (h->cooperative) {
     void* args[] = {&p};
@@ -595,7 +629,7 @@ int pfb200_debug_profile(pfb200_handle* h, long long* out, int max_ctas) {
   int n = h->prob.n_groups * h->prob.G;
   if (n > max_ctas) n = max_ctas;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  CUDA_TRY(cudaMemcpy(out, h->prof.ptr, (size_t)n * 12 * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out, h->prof.ptr, (size_t)n * kProfSlots * 8, cudaMemcpyDeviceToHost));
   return n;
 }
 

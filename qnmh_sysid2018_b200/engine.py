@@ -189,7 +189,7 @@ class Engine(object):
 
     def debug_profile(self, max_ctas=4096):
         """(n_ctas, 12) cycle counters per phase; all zero unless built with -DPFB_PROFILE."""
-        buf = np.zeros((max_ctas, 12), dtype=np.int64)
+        buf = np.zeros((max_ctas, 16), dtype=np.int64)
         n = self._lib.pfb200_debug_profile(self._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), max_ctas)
         if n < 0:
             L.check(n)

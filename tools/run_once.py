@@ -20,12 +20,16 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--G", type=int, default=0)
 ap.add_argument("--no-smoother", action="store_true")
 ap.add_argument("--inject", action="store_true")
+ap.add_argument("--opt", action="append", default=[], help="name=value engine option")
 a = ap.parse_args()
 theta = bench.THETA_LGSS if a.model == "lgss" else bench.THETA_SV
 obs = bench.synthetic_obs(a.model, a.T)
 eng = Engine(a.model, a.dtype, 0)
 if a.G:
     eng.set_option("ctas_per_filter", a.G)
+for o in a.opt:
+    k, v = o.split("=")
+    eng.set_option(k, int(v))
 draws = None
 if a.inject:
     from oracle import pf_oracle as orc
@@ -43,8 +47,8 @@ print("N=%d T=%d B=%d %s G=%d groups=%d: kernel ms %s -> %.2f G particle-steps/s
          ["%.3f" % m for m in ms], units / min(ms) / 1e6, min(ms) * 1e3 / a.T, ll[0]))
 prof = eng.debug_profile()
 if prof.any():
-    names = ["A:scan(+rest)", "block_sum", "exchange1", "prefix+bounds", "children", "block_max", "exchange2", "xchg_max", "A:load+exp", "A:smooth", "B:normalise"]
+    names = ["A:scan(+rest)", "block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait", "xchg_max", "A:load+exp", "smooth@X1", "smooth@X2", "ch:search", "ch:gather", "ch:rng", "ch:model", "ch:store"]
     per_step = prof / float(a.T) / 1.965e3  # us at 1965 MHz
     for i, nm in enumerate(names):
         print("   %-20s mean %7.2f us  max %7.2f us  min %7.2f us" % (nm, per_step[:, i].mean(), per_step[:, i].max(), per_step[:, i].min()))
-    print("   total (mean over CTAs) %.2f us/step" % per_step.sum(axis=1).mean())
+    print("   total (mean over CTAs) %.2f us/step" % per_step[:, :11].sum(axis=1).mean())
