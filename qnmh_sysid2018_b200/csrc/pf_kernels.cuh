@@ -75,7 +75,9 @@ struct DeviceProblem {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, typename Real, int BLOCK, int ITEMS>
+// GENERAL = false compiles the production flavour only: Philox noise + systematic resampling (the
+// injected-randomness and stratified paths, and their registers, are compiled out).
+template <int MODEL, typename Real, int BLOCK, int ITEMS, bool GENERAL>
 struct PfKernel {
   using Ops = ModelOps<MODEL, Real>;
   static constexpr int kChunk = BLOCK * ITEMS;  // parents per scan sub-chunk (ITEMS odd: the
@@ -157,18 +159,20 @@ struct PfKernel {
     exchange_wait();
   }
 
-  __device__ double xchg_max() {  // order independent
+  // max over the exchanged values; every warp reduces all G values itself (no block barrier)
+  __device__ double xchg_max() {
     double m = -INFINITY;
-    for (int i = tid; i < p.G; i += BLOCK) m = dmax(m, sh_x[i]);
-    return block_max(m);
+    for (int i = lane; i < p.G; i += 32) m = dmax(m, sh_x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = dmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
   }
 
-  // Prefix sums of sh_x in a fixed order.  incl(i) = offset of the lane segment holding i (a
-  // shuffle scan of the segment totals) + the running sum inside the segment; every CTA evaluates
-  // the same function on the same array, so neighbouring CTAs agree bit for bit on their common
-  // boundary: excl(g) := incl(g-1).  Results land in sh_red[0..2] = (excl, incl, total); the caller
-  // synchronises.
-  __device__ void xchg_prefix_warp0() {
+  // Prefix sums of sh_x in a fixed order, evaluated redundantly by every warp (same bits in all
+  // warps and all CTAs; no block barrier).  incl(i) = offset of the lane segment holding i (a
+  // shuffle scan of the segment totals) + the running sum inside the segment, so neighbouring CTAs
+  // agree bit for bit on their common boundary: excl(g) := incl(g-1).
+  __device__ void xchg_prefix(double& excl, double& incl, double& total) {
     const int G = p.G;
     const int W = (G + 31) / 32;
     const int b0 = lane * W;
@@ -194,21 +198,34 @@ struct PfKernel {
     const unsigned wp = __ballot_sync(0xffffffffu, hp);
     const unsigned wc = __ballot_sync(0xffffffffu, hc);
     const unsigned wt = __ballot_sync(0xffffffffu, ht);
-    vp = wp ? __shfl_sync(0xffffffffu, vp, __ffs(wp) - 1) : 0.0;
-    vc = __shfl_sync(0xffffffffu, vc, __ffs(wc) - 1);
-    vt = __shfl_sync(0xffffffffu, vt, __ffs(wt) - 1);
-    if (lane == 0) { sh_red[0] = vp; sh_red[1] = vc; sh_red[2] = vt; }
+    excl = wp ? __shfl_sync(0xffffffffu, vp, __ffs(wp) - 1) : 0.0;
+    incl = __shfl_sync(0xffffffffu, vc, __ffs(wc) - 1);
+    total = __shfl_sync(0xffffffffu, vt, __ffs(wt) - 1);
   }
 
+  // block-wide max; ends WITHOUT a trailing barrier: the caller must synchronise before sh_red is
+  // reused (exchange_arrive does)
   __device__ double block_max(double v) {
-    v = warp_max(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if (lane == 0) sh_red[warp] = v;
     __syncthreads();
     double r = (lane < kWarps) ? sh_red[lane] : -INFINITY;  // every warp reduces the same values
-    r = warp_max(r);
-    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = dmax(r, __shfl_xor_sync(0xffffffffu, r, o));
     return r;
+  }
+
+  // block-wide sum of one value (fixed tree), valid in every thread; same barrier contract as
+  // block_max
+  __device__ double block_sum1(double v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh_red[warp] = v;
+    __syncthreads();
+    const double r = (lane < kWarps) ? sh_red[lane] : 0.0;
+    return warp_sum(r);
   }
 
   // sums K accumulators over the block; result valid in thread 0 (fixed tree): warp shuffles, then
@@ -383,8 +400,8 @@ struct PfKernel {
   __device__ __forceinline__ double position(int n, double u, int t, const double* inj_u_t,
                                              unsigned long long eval_id) const {
     double a;
-    if (p.resampling == 1) {
-      u = p.inject ? ld_cg(inj_u_t + n) : philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)n);
+    if ((GENERAL && p.resampling == 1)) {
+      u = (GENERAL && p.inject) ? ld_cg(inj_u_t + n) : philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)n);
       a = __dadd_rn(u, (double)n);
     } else {
       a = __dadd_rn((double)n, u);
@@ -397,7 +414,7 @@ struct PfKernel {
                                    unsigned long long eval_id) const {
     const int N = p.N;
     if (!(c == c)) return N;  // NaN CDF (all weights zero): nothing to assign
-    double est = ceil(c * (double)N - (p.resampling == 1 ? 0.5 : u));
+    double est = ceil(c * (double)N - ((GENERAL && p.resampling == 1) ? 0.5 : u));
     int n = est < 0.0 ? 0 : (est > (double)N ? N : (int)est);
     while (n > 0 && !(position(n - 1, u, t, inj_u_t, eval_id) < c)) --n;
     while (n < N && position(n, u, t, inj_u_t, eval_id) < c) ++n;
@@ -472,7 +489,7 @@ struct PfKernel {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
         Real z0, z1;
-        if (p.inject) {
+        if ((GENERAL && p.inject)) {
           const int n = nb + 2 * h;
           z0 = (n >= n_lo && n < n_hi) ? (Real)ld_cg(inj_z_t + n) : (Real)0;
           z1 = (n + 1 >= n_lo && n + 1 < n_hi) ? (Real)ld_cg(inj_z_t + n + 1) : (Real)0;
@@ -525,10 +542,10 @@ struct PfKernel {
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const unsigned long long eval_id = p.eval_ids[b];
     const size_t ib = p.inject_per_filter ? (size_t)b : 0;
-    const double* inj_z0 = p.inject ? p.inj_z0 + ib * N : nullptr;
-    const size_t u_row = (p.resampling == 1) ? (size_t)N : 1;
-    const double* inj_u = p.inject ? p.inj_u + ib * (T + 1) * u_row : nullptr;
-    const double* inj_z = p.inject ? p.inj_z + ib * (size_t)(T + 1) * N : nullptr;
+    const double* inj_z0 = (GENERAL && p.inject) ? p.inj_z0 + ib * N : nullptr;
+    const size_t u_row = ((GENERAL && p.resampling == 1)) ? (size_t)N : 1;
+    const double* inj_u = (GENERAL && p.inject) ? p.inj_u + ib * (T + 1) * u_row : nullptr;
+    const double* inj_z = (GENERAL && p.inject) ? p.inj_z + ib * (size_t)(T + 1) * N : nullptr;
 
     __syncthreads();
     if (tid < kNumConsts) sh_c[tid] = p.consts[(size_t)b * kNumConsts + tid];
@@ -544,12 +561,12 @@ struct PfKernel {
     // ---- generation 0 (standard.py:62-67): stationary draw or fixed value, uniform weights
     for (int pp = (j_begin >> 1) + tid; pp < ((j_end + 1) >> 1); pp += BLOCK) {
       Real z[2] = {0, 0};
-      if (p.gen_init && !p.inject) philox_normal_pair<Real>(p.seed, eval_id, 0u, (uint32_t)pp, z[0], z[1]);
+      if (p.gen_init && !(GENERAL && p.inject)) philox_normal_pair<Real>(p.seed, eval_id, 0u, (uint32_t)pp, z[0], z[1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int n = 2 * pp + e;
         if (n >= j_begin && n < j_end) {
-          if (p.gen_init && p.inject) z[e] = (Real)ld_cg(inj_z0 + n);
+          if (p.gen_init && (GENERAL && p.inject)) z[e] = (Real)ld_cg(inj_z0 + n);
           xr[n] = p.gen_init ? Ops::init(sh_c, z[e]) : (Real)p.initial_state;
           lwr[n] = (Real)0;
           if (p.ws_per_filter) ar[n] = 0;  // generation-0 ancestors are never followed
@@ -578,17 +595,17 @@ struct PfKernel {
       const double* inj_u_t = nullptr;
       const double* inj_z_t = nullptr;
       if (!final_step) {
-        if (p.inject) {
+        if ((GENERAL && p.inject)) {
           inj_u_t = inj_u + (size_t)t * u_row;
           inj_z_t = inj_z + (size_t)t * N;
-          u = (p.resampling == 1) ? 0.0 : ld_cg(inj_u_t);
-        } else if (p.resampling == 0) {
+          u = ((GENERAL && p.resampling == 1)) ? 0.0 : ld_cg(inj_u_t);
+        } else if ((!GENERAL || p.resampling == 0)) {
           u = philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, 0u);
         }
         y_obs = __ldg(obs + t);
         y_prop = p.svl_obs_model ? __ldg(obs + t - 1) : y_obs;  // Q10
       } else {
-        u = p.inject ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
+        u = (GENERAL && p.inject) ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
       }
 
 #ifdef PFB_PROFILE
@@ -608,9 +625,8 @@ struct PfKernel {
       }
       PFB_TICK(0);
       {
-        double red[1] = {accF};
-        block_sum(red);
-        if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * G + g] = red[0];
+        const double f = block_sum1(accF);
+        if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * G + g] = f;
       }
       PFB_TICK(1);
       exchange_arrive(A);
@@ -618,25 +634,19 @@ struct PfKernel {
       PFB_TICK(9);
       exchange_wait();
       PFB_TICK(2);
-      // prefix over the group + this CTA's children range; lanes 0 / 1 of warp 0 evaluate the two
-      // boundaries side by side
-      if (warp == 0) {
-        xchg_prefix_warp0();
-        __syncwarp();
-        const double Pg_ = sh_red[0], Pg1_ = sh_red[1], S_ = sh_red[2];
-        const double invS_ = 1.0 / S_;  // the CDF is (prefix sum) * (1/S) everywhere
-        if (!final_step && lane < 2) {
-          int nb;
-          if (lane == 0) nb = (g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg_, invS_), u, t, inj_u_t, eval_id);
-          else nb = last_cta ? N : lower_bound_child(__dmul_rn(Pg1_, invS_), u, t, inj_u_t, eval_id);
-          reinterpret_cast<int*>(sh_red + 4)[lane] = nb;
-        }
-        if (lane == 0) sh_red[3] = invS_;
+      // prefix over the group + this CTA's children range, evaluated by every warp on its own
+      // (lanes 0 / 1 take the two boundaries side by side): no block barrier on the critical path
+      double Pg, Pg1, S;
+      xchg_prefix(Pg, Pg1, S);
+      const double invS = 1.0 / S;  // the CDF is (prefix sum) * (1/S) everywhere
+      int n_begin = 0, n_end = 0;
+      if (!final_step) {
+        int nb = 0;
+        if (lane == 0) nb = (g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg, invS), u, t, inj_u_t, eval_id);
+        if (lane == 1) nb = last_cta ? N : lower_bound_child(__dmul_rn(Pg1, invS), u, t, inj_u_t, eval_id);
+        n_begin = __shfl_sync(0xffffffffu, nb, 0);
+        n_end = __shfl_sync(0xffffffffu, nb, 1);
       }
-      __syncthreads();
-      const double Pg = sh_red[0], S = sh_red[2], invS = sh_red[3];
-      const int n_begin = final_step ? 0 : reinterpret_cast<int*>(sh_red + 4)[0];
-      const int n_end = final_step ? 0 : reinterpret_cast<int*>(sh_red + 4)[1];
       if (g == 0 && tid == 0) {
         p.stat_m[(size_t)b * (T + 1) + tau] = m;
         p.stat_S[(size_t)b * (T + 1) + tau] = S;
@@ -749,12 +759,12 @@ struct PfKernel {
   }
 };
 
-template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB>
+template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB, bool GENERAL>
 __global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const DeviceProblem prob) {
   extern __shared__ double pf_smem[];
   __shared__ double sh_red[9 * 32 + 8];
   __shared__ double sh_c[kNumConsts];
-  PfKernel<MODEL, Real, BLOCK, ITEMS> k(prob, pf_smem, sh_red, sh_c);
+  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c);
   for (int b = k.q; b < prob.B; b += prob.n_groups) {
     k.run_filter(b);
     if (k.aborted) return;

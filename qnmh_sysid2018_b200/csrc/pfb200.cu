@@ -80,13 +80,13 @@ constexpr int kChunk = kBlock * kItems;
 
 typedef void (*KernelFn)(const DeviceProblem);
 
-template <typename Real>
+template <typename Real, bool GENERAL>
 KernelFn kernel_for_model(int model) {
   switch (model) {
-    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems, kMinB>;
+    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems, kMinB, GENERAL>;
 #ifndef PFB_LGSS_ONLY
-    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems, kMinB>;
-    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems, kMinB>;
+    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems, kMinB, GENERAL>;
+    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems, kMinB, GENERAL>;
 #endif
   }
   return nullptr;
@@ -134,7 +134,9 @@ struct pfb200_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false;
-  KernelFn kernel = nullptr;
+  KernelFn kernel = nullptr;          // flavour selected by the configured problem
+  KernelFn kernel_fast = nullptr;     // Philox + systematic resampling
+  KernelFn kernel_general = nullptr;  // + injected randomness, stratified resampling
   // options
   long long opt_ctas_per_filter = 0;
   long long opt_max_groups = 0;
@@ -194,7 +196,9 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   h->model = model_id;
   h->dtype = dtype;
   h->P = P;
-  h->kernel = dtype == PFB200_F64 ? kernel_for_model<double>(model_id) : kernel_for_model<float>(model_id);
+  h->kernel_fast = dtype == PFB200_F64 ? kernel_for_model<double, false>(model_id) : kernel_for_model<float, false>(model_id);
+  h->kernel_general = dtype == PFB200_F64 ? kernel_for_model<double, true>(model_id) : kernel_for_model<float, true>(model_id);
+  h->kernel = h->kernel_fast;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -306,6 +310,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const bool inject = n_inj == 4;
   const bool history = (flags & PFB200_FLAG_STORE_HISTORY) != 0;
   CUDA_TRY(cudaSetDevice(h->device));
+
+  h->kernel = (inject || resampling != PFB200_RESAMPLE_SYSTEMATIC) ? h->kernel_general : h->kernel_fast;
 
   // ---- launch geometry
   const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
