@@ -70,39 +70,76 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons DURING the timed region: NVML in-process every 20 ms
+    (nvidia-smi every 200 ms as fallback)."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+            ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, set of active reasons)
+        self.sm_max = None
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if uuid:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, handle)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        pynvml, handle = self.nvml
+        mhz = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        try:
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+        except Exception:
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+        self.samples.append((mhz, {n for n, b in self.BITS if mask & b}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            self.sm_max = float(f[1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.samples.append((float(f[0]), {n for i, n in enumerate(names) if f[2 + i] == "Active"}))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted(set().union(*[s[1] for s in self.samples]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,7 +270,11 @@ def gpu_arm(args):
     for _ in range(args.warmup):
         eng.execute()
     barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -332,7 +373,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
