@@ -1,5 +1,2 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-python tools/run_once.py --T 200 2>&1 | tail -1
-python tools/run_once.py --T 200 --N 2000 2>&1 | tail -1
-python tools/run_once.py --T 200 --N 65536 --model sv 2>&1 | tail -1
-python tools/run_once.py --T 100 --N 4096 --B 1024 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_distributed.py -x -q 2>&1 | tail -15
+timeout 600 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_distributed.py 2>&1 | tail -3

@@ -88,7 +88,8 @@ int pfb200_set_stream(pfb200_handle* h, void* cuda_stream);
 /* Tuning knobs (defaults are chosen from the problem size):
  *   "ctas_per_filter"  G: CTAs cooperating on one filter (0 = automatic)
  *   "max_groups"       upper bound on concurrently resident filter groups (0 = automatic)
- *   "spin_limit"       abort a launch whose inter-CTA exchange spins longer than this many polls */
+ *   "spin_limit"       abort a launch whose inter-CTA exchange spins longer than this many polls
+ *   "dist_world", "dist_rank"  shard ONE filter over several GPUs (see pfb200_dist_* below) */
 int pfb200_set_option(pfb200_handle* h, const char* name, long long value);
 int pfb200_get_info(pfb200_handle* h, const char* name, long long* value);
 
@@ -165,6 +166,23 @@ int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int
  * t = -1: the trajectory-draw uniform). */
 int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int count,
                            double* u);
+
+/*
+ * One filter sharded over the GPUs of a box (one process per GPU).  Rank r holds the particles with
+ * global indices [r*span, (r+1)*span); children are written to the owner of their index range with
+ * NVLink peer stores, the per-step exchange (tile totals, max log-weight) is an all-gather through
+ * peer memory inside the persistent kernel.  Protocol, identical on every rank:
+ *   pfb200_set_option(h, "dist_world", R); pfb200_set_option(h, "dist_rank", r);
+ *   pfb200_configure(h, 1, N_global, ...)            -- same arguments on all ranks
+ *   pfb200_dist_export(h, mine, bytes)               -- bytes = pfb200_dist_handle_bytes()
+ *   (all-gather the R handle blobs between the processes, e.g. torch.distributed)
+ *   pfb200_dist_connect(h, all, R); (host barrier); pfb200_execute(h) on all ranks; pfb200_fetch
+ * filt / smo / grad_terms of a rank are its PARTIAL sums (add them over ranks); log_like is complete
+ * and identical on every rank; traj_index is -1.
+ */
+int pfb200_dist_handle_bytes(void);
+int pfb200_dist_export(pfb200_handle* h, void* handles_out, int bytes);
+int pfb200_dist_connect(pfb200_handle* h, const void* all_handles, int world);
 
 /* Debug builds (-DPFB_PROFILE) only: per-CTA cycle counters of 12 phases of a time step, summed
  * over the launch; out[cta][12].  Returns the number of CTAs written (or a negative error). */

@@ -44,6 +44,9 @@ SIGNATURES = {
     "pfb200_run": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                              C.c_uint, _dp, _dp, C.c_uint64, _up, _dp, _dp, _dp, _dp,
                              _dp, _dp, _dp, _dp, _ip, _dp]),
+    "pfb200_dist_handle_bytes": (C.c_int, []),
+    "pfb200_dist_export": (C.c_int, [_H, C.c_void_p, C.c_int]),
+    "pfb200_dist_connect": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "pfb200_debug_profile": (C.c_int, [_H, C.POINTER(C.c_longlong), C.c_int]),
     "pfb200_philox_normals": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),
     "pfb200_philox_uniforms": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),

@@ -45,6 +45,10 @@ struct DeviceProblem {
   int G;         // CTAs per filter group
   int n_groups;  // groups resident in this launch
   int per_cta;   // parents owned by one CTA
+  // distributed single filter: R ranks (GPUs), G = R * G_loc CTAs, rank r owns the global indices
+  // [r*span, (r+1)*span); its rings hold only those.  R = 1: single GPU (G_loc = G, span >= N).
+  int R, rank, G_loc, span;
+  unsigned epoch0;  // exchanges completed by earlier launches (peer counters are never reset)
   int tile_cap;  // shared-memory CDF tile capacity (entries, multiple of the sub-chunk size)
   int RX, RA, RW;  // ring depths: particles, ancestors, log-weights
   int do_smoother, gen_init, resampling, svl_obs_model;
@@ -72,6 +76,12 @@ struct DeviceProblem {
   int* traj_k;        // [B]
   int* traj_idx;      // [B]
   long long* prof;    // [grid][kProfSlots] per-phase cycle counters (PFB_PROFILE builds only)
+  // peer-memory views of every rank's rings / exchange buffers (entry `rank` = own memory)
+  void* peer_x[8];
+  void* peer_lw[8];
+  int* peer_anc[8];
+  double* peer_xval[8];
+  unsigned* peer_xcount[8];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,7 +100,9 @@ struct PfKernel {
   double* sh_x;    // [G] exchange staging
   double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
-  const int tid, lane, warp, g, q;
+  const int tid, lane, warp, g_loc, q, g;  // g: CTA index inside the (possibly multi-GPU) group
+  const bool dist;                         // several GPUs work on this filter
+  const int lo;                            // first global particle index held by this rank
   const bool pow2N;
   const double invN;
   unsigned epoch;
@@ -102,9 +114,10 @@ struct PfKernel {
 
   __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst)
       : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst), tid(threadIdx.x),
-        lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g(blockIdx.x % prob.G),
-        q(blockIdx.x / prob.G), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
-        epoch(0), aborted(false) {}
+        lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g_loc(blockIdx.x % prob.G_loc),
+        q(blockIdx.x / prob.G_loc), g(prob.rank * prob.G_loc + blockIdx.x % prob.G_loc),
+        dist(GENERAL && prob.R > 1), lo(prob.rank * prob.span), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
+        epoch(prob.epoch0), aborted(false) {}
 
   // ---- inter-CTA exchange (all-gather of one double per CTA + group barrier).  Arrival is a
   //      release-increment of one counter per group; ONE thread per CTA polls it (G pollers on one
@@ -118,12 +131,17 @@ struct PfKernel {
       return;
     }
     ++epoch;
-    double* val = p.xval + ((size_t)q * 2 + (epoch & 1u)) * G;
-    unsigned* cnt = p.xcount + (size_t)q * 32;
     __syncthreads();  // all global writes of this CTA precede the release below
-    if (tid == 0) {
-      val[g] = v;
-      red_release_add_u32(cnt, 1u);
+    if (dist) {
+      // all-gather across GPUs: write the value into every rank's buffer and release-increment
+      // every rank's counter at system scope (NVLink peer stores); thread r serves rank r
+      if (tid < p.R) {
+        p.peer_xval[tid][(size_t)(epoch & 1u) * G + g] = v;
+        red_release_sys_add_u32(p.peer_xcount[tid], 1u);
+      }
+    } else if (tid == 0) {
+      p.xval[((size_t)q * 2 + (epoch & 1u)) * G + g] = v;
+      red_release_add_u32(p.xcount + (size_t)q * 32, 1u);
     }
   }
 
@@ -141,7 +159,7 @@ struct PfKernel {
     if (tid == 0) {
       const unsigned target = epoch * (unsigned)G;
       long long spins = 0;
-      while ((int)(ld_acquire_u32(cnt) - target) < 0) {
+      while ((int)((dist ? ld_acquire_sys_u32(cnt) : ld_acquire_u32(cnt)) - target) < 0) {
         if ((++spins & 1023) == 0 && (spins > p.spin_limit || ld_relaxed_i32(p.abort_flag) != 0)) {
           atomicExch(p.abort_flag, 1);
           ab = 1;
@@ -319,6 +337,15 @@ struct PfKernel {
   //      (standard.py:146-169).  The weights s[j] = exp(logw_tau[j] - m_tau) are recomputed from
   //      the log-weight ring, so the job only reads data that is final and can run while the CTA
   //      waits for an exchange.
+  // element n (global index) of ring row `slot`: own memory, or the owner rank's memory over NVLink
+  template <typename T>
+  __device__ __forceinline__ T ld_ring(const T* local_row_view, T* const* peer_base, int slot, int n,
+                                       uint64_t pol) const {
+    if (!dist || (unsigned)(n - lo) < (unsigned)p.span) return ld_hint(local_row_view + n, pol);
+    const int r = n / p.span;
+    return ld_sys(peer_base[r] + (size_t)slot * p.NS + (n - r * p.span));
+  }
+
   template <int NI>
   __device__ void smooth_chunk(const Real* lw, double m_tau, const Real* xr, const int* ar,
                                const double* obs, int tau, int i, int c0, int len,
@@ -334,24 +361,25 @@ struct PfKernel {
       nxt[k] = cur[k];
       l[k] = (jl < len) ? ld_hint(lw + c0 + jl, once) : (Real)(-INFINITY);
     }
-    const int* a = ar + (size_t)(tau % p.RA) * NS;
-    const int* a_wrap = ar + (size_t)(p.RA - 1) * NS;
+    int slot = tau % p.RA;
+    const int* a = ar + (size_t)slot * NS;
     for (int lvl = tau; lvl > i; --lvl) {
 #pragma unroll
       for (int k = 0; k < NI; ++k) {
         nxt[k] = cur[k];
-        cur[k] = ld_hint(a + cur[k], keep);
+        cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
       }
-      a = (a == ar) ? a_wrap : a - NS;
+      if (slot == 0) { slot = p.RA - 1; a = ar + (size_t)slot * NS; } else { --slot; a -= NS; }
     }
-    const Real* xi = xr + (size_t)(i % p.RX) * NS;
-    const Real* xn = xr + (size_t)((i + 1) % p.RX) * NS;
+    const int si = i % p.RX, sn = (i + 1) % p.RX;
+    const Real* xi = xr + (size_t)si * NS;
+    const Real* xn = xr + (size_t)sn * NS;
     const double y = __ldg(obs + i);
     Real xc[NI], xnext[NI];
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
-      xc[k] = ld_hint(xi + cur[k], once);
-      xnext[k] = ld_hint(xn + nxt[k], once);
+      xc[k] = ld_ring<Real>(xi, reinterpret_cast<Real* const*>(p.peer_x), si, cur[k], once);
+      xnext[k] = ld_ring<Real>(xn, reinterpret_cast<Real* const*>(p.peer_x), sn, nxt[k], once);
     }
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
@@ -391,7 +419,7 @@ struct PfKernel {
   __device__ void write_smooth_partials(int b, int i, double (&acc)[kMaxParams + 1]) {
     block_sum(acc);
     if (tid == 0) {
-      double* dst = p.smo_part + (((size_t)b * (p.T + 1) + i) * p.G + g) * (p.P + 1);
+      double* dst = p.smo_part + (((size_t)b * (p.T + 1) + i) * p.G_loc + g_loc) * (p.P + 1);
       for (int k = 0; k <= p.P; ++k) dst[k] = acc[k];
     }
   }
@@ -454,7 +482,7 @@ struct PfKernel {
   __device__ void children_chunk(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
                                  int* anc_new, const double* inj_z_t, const double* inj_u_t, int t,
                                  double u, unsigned long long eval_id, double y_prop, double y_obs,
-                                 int c0, int len, int n_lo, int n_hi, double& mx) {
+                                 int c0, int len, int n_lo, int n_hi, bool remote, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
     int top = 1;
     while (top * 2 <= len) top *= 2;
@@ -513,12 +541,41 @@ struct PfKernel {
           mx = dmax(mx, dmax((double)la, (double)lb));
           store2(x_new + n, xa, xb);
           store2(lw_new + n, la, lb);
-          st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
+          if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(c0 + j[2 * h], c0 + j[2 * h + 1]);
+          else st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
         } else {
-          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
-          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
+          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
         }
         PFB_TICK(15);
+      }
+    }
+  }
+
+  // children [n_lo, n_hi) of the tile, written to the rank that owns their index range (own rings,
+  // or a peer's rings through NVLink stores when the filter is distributed)
+  __device__ void children_all(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
+                               int* anc_new, const double* inj_z_t, const double* inj_u_t, int t,
+                               double u, unsigned long long eval_id, double y_prop, double y_obs,
+                               int c0, int len, int n_lo, int n_hi, double& mx) {
+    if (!dist) {
+      children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
+                     y_obs, c0, len, n_lo, n_hi, false, mx);
+      return;
+    }
+    if (n_hi <= n_lo) return;
+    const size_t NS = (size_t)p.NS;
+    for (int r = n_lo / p.span; r < p.R && r * p.span < n_hi; ++r) {
+      const int s_lo = max(n_lo, r * p.span), s_hi = min(n_hi, (r + 1) * p.span);
+      if (r == p.rank) {
+        children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
+                       y_obs, c0, len, s_lo, s_hi, false, mx);
+      } else {  // global-index views of rank r's generation-t rows
+        Real* xv = reinterpret_cast<Real*>(p.peer_x[r]) + (size_t)(t % p.RX) * NS - (size_t)r * p.span;
+        Real* lv = reinterpret_cast<Real*>(p.peer_lw[r]) + (size_t)(t % p.RW) * NS - (size_t)r * p.span;
+        int* av = p.peer_anc[r] + (size_t)(t % p.RA) * NS - (size_t)r * p.span;
+        children_chunk(tile, x_prev, xv, lv, av, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs, c0,
+                       len, s_lo, s_hi, true, mx);
       }
     }
   }
@@ -533,12 +590,14 @@ struct PfKernel {
 
   // ---- one filter evaluation (all T steps) -------------------------------------------------
   __device__ void run_filter(int b) {
-    const int N = p.N, T = p.T, L = p.L, G = p.G, P = p.P;
+    const int N = p.N, T = p.T, L = p.L;
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
-    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS;
-    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS;
-    int* ar = p.anc_ring + (size_t)ws * p.RA * NS;
+    // ring rows are addressed with GLOBAL particle indices: the views are shifted by the first index
+    // this rank holds (0 on a single GPU)
+    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS - lo;
+    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS - lo;
+    int* ar = p.anc_ring + (size_t)ws * p.RA * NS - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const unsigned long long eval_id = p.eval_ids[b];
     const size_t ib = p.inject_per_filter ? (size_t)b : 0;
@@ -626,7 +685,7 @@ struct PfKernel {
       PFB_TICK(0);
       {
         const double f = block_sum1(accF);
-        if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * G + g] = f;
+        if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * p.G_loc + g_loc] = f;
       }
       PFB_TICK(1);
       exchange_arrive(A);
@@ -647,7 +706,7 @@ struct PfKernel {
         n_begin = __shfl_sync(0xffffffffu, nb, 0);
         n_end = __shfl_sync(0xffffffffu, nb, 1);
       }
-      if (g == 0 && tid == 0) {
+      if (g_loc == 0 && tid == 0) {
         p.stat_m[(size_t)b * (T + 1) + tau] = m;
         p.stat_S[(size_t)b * (T + 1) + tau] = S;
       }
@@ -692,8 +751,8 @@ struct PfKernel {
           for (int jl = tid; jl < own; jl += BLOCK)
             if (sh_s[jl] <= u) ++traj_cnt;
         } else {
-          children_chunk(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
-                         y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
+          children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
+                       y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
         }
       } else {
         int n_cursor = n_begin;
@@ -723,8 +782,8 @@ struct PfKernel {
               n_hi = lower_bound_child(__dmul_rn(next_base, invS), u, t, inj_u_t, eval_id);
               n_hi = max(n_cursor, min(n_hi, n_end));
             }
-            children_chunk(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
-                           y_prop, y_obs, c0, len, n_cursor, n_hi, mx);
+            children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
+                         y_prop, y_obs, c0, len, n_cursor, n_hi, mx);
             n_cursor = n_hi;
           }
           base += chunk_total;
@@ -734,10 +793,11 @@ struct PfKernel {
         const int cnt = block_sum_int(traj_cnt);
         if (tid == 0 && cnt) atomicAdd(p.traj_k + b, cnt);
         exchange(0.0);  // all counts are in; also fences the workspace before the next filter
-        if (g == 0 && tid == 0) {
+        if (g_loc == 0 && tid == 0) {
           int k = ld_cg(p.traj_k + b);
           if (k > N - 1) k = N - 1;
-          p.traj_idx[b] = ld_cg(ar + (size_t)(T % p.RA) * NS + k);
+          // distributed: the count is a per-rank partial and the row may live elsewhere (not drawn)
+          p.traj_idx[b] = dist ? -1 : ld_cg(ar + (size_t)(T % p.RA) * NS + k);
         }
       } else {
         PFB_TICK(4);

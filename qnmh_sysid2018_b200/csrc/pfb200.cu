@@ -143,6 +143,11 @@ struct pfb200_handle {
   long long opt_spin_limit = 20000000LL;
   long long opt_l2_persist = 0;   // pin the ancestor ring in L2 (access policy window)
   size_t l2_persist_max = 0, l2_window_max = 0;
+  // distributed single filter (one process per GPU, peer memory over NVLink)
+  long long opt_dist_world = 1, opt_dist_rank = 0;
+  bool dist_connected = false;
+  unsigned dist_epoch = 0;
+  void* peer_opened[8][5] = {};  // IPC mappings to close
   // configured problem
   bool configured = false;
   bool executed = false;
@@ -159,6 +164,12 @@ struct pfb200_handle {
   std::vector<double> h_consts;
   std::vector<unsigned long long> h_evals;
 };
+
+static void dist_close(pfb200_handle* h) {
+  for (int r = 0; r < 8; ++r)
+    for (int k = 0; k < 5; ++k)
+      if (h->peer_opened[r][k]) { cudaIpcCloseMemHandle(h->peer_opened[r][k]); h->peer_opened[r][k] = nullptr; }
+}
 
 extern "C" {
 
@@ -218,6 +229,7 @@ int pfb200_destroy(pfb200_handle* h) {
   if (!h) return PFB200_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  dist_close(h);
   DevBuf* bufs[] = {&h->obs, &h->consts, &h->evals, &h->inj_z0, &h->inj_u, &h->inj_z, &h->inj_uf, &h->x_ring,
                     &h->logw, &h->anc, &h->xval, &h->xcount, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
                     &h->smo_part, &h->traj_k, &h->traj_idx, &h->ll_terms, &h->log_like, &h->filt, &h->smo,
@@ -244,6 +256,10 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
   else if (!strcmp(name, "max_groups")) h->opt_max_groups = value;
   else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
   else if (!strcmp(name, "l2_persist")) h->opt_l2_persist = value;
+  else if (!strcmp(name, "dist_world")) {
+    if (value < 1 || value > 8) return fail(PFB200_EINVAL, "pfb200_set_option: dist_world must be 1..8");
+    h->opt_dist_world = value;
+  } else if (!strcmp(name, "dist_rank")) h->opt_dist_rank = value;
   else return fail(PFB200_EINVAL, "pfb200_set_option: unknown option '%s'", name);
   h->configured = false;
   return PFB200_OK;
@@ -258,6 +274,8 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "block_threads")) *value = kBlock;
   else if (!strcmp(name, "chunk")) *value = kChunk;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
+  else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
+  else if (!strcmp(name, "span")) *value = h->prob.span;
   else if (!strcmp(name, "l2_persist_max")) *value = (long long)h->l2_persist_max;
   else if (!strcmp(name, "l2_window_max")) *value = (long long)h->l2_window_max;
   else if (!strcmp(name, "blocks_per_sm")) *value = h->blocks_per_sm;
@@ -317,7 +335,15 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
   const size_t smem_limit = 200 * 1024;  // dynamic shared memory we are willing to use per CTA
   CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-  int G = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0;
+  const int R = (int)h->opt_dist_world, rank = (int)h->opt_dist_rank;
+  if (R > 1) {
+    if (rank < 0 || rank >= R) return fail(PFB200_EINVAL, "pfb200_configure: dist_rank %d out of range for dist_world %d", rank, R);
+    if (B != 1 || history)
+      return fail(PFB200_EINVAL, "pfb200_configure: a distributed filter takes n_filters = 1 and no STORE_HISTORY");
+    h->kernel = h->kernel_general;  // the peer-memory paths live in the general flavour
+  }
+  h->dist_connected = false;
+  int G = 1, G_loc = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0;
   size_t smem = 0;
   for (int pass = 0; pass < 3; ++pass) {
     // shared memory of the current guess -> co-resident CTAs -> group size
@@ -325,14 +351,17 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
     if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
     capacity = bps * h->num_sms;
-    if (h->opt_ctas_per_filter > 0) G = (int)h->opt_ctas_per_filter;
-    else if (B == 1) G = (N + kBlock - 1) / kBlock;
-    else G = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
-    if (G > capacity) G = capacity;
-    if (G > 1024) G = 1024;
-    if (G < 1) G = 1;
+    if (h->opt_ctas_per_filter > 0) G_loc = (int)h->opt_ctas_per_filter;
+    else if (B == 1) G_loc = ((N + R - 1) / R + kBlock - 1) / kBlock;
+    else G_loc = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
+    if (G_loc > capacity) G_loc = capacity;
+    if (G_loc * R > 1024) G_loc = 1024 / R;
+    if (G_loc < 1) G_loc = 1;
+    G = G_loc * R;
     per = (N + G - 1) / G;
-    G = (N + per - 1) / per;  // no empty CTAs
+    if (G > 1) per = (per + 31) & ~31;  // tile boundaries on 32-particle multiples (aligned stores on
+                                        // every rank; same tiling for any split of G over GPUs)
+    if (R == 1) { G = (N + per - 1) / per; G_loc = G; }  // no empty CTAs on a single GPU
     const int n_chunks = (per + kChunk - 1) / kChunk;
     const size_t want = (size_t)n_chunks * kChunk;
     tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : kChunk;
@@ -341,15 +370,15 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
   capacity = bps * h->num_sms;
-  if (G > capacity)
-    return fail(PFB200_ECUDA, "pfb200_configure: %d cooperating CTAs exceed the %d co-resident CTAs", G, capacity);
+  if (G_loc > capacity)
+    return fail(PFB200_ECUDA, "pfb200_configure: %d cooperating CTAs exceed the %d co-resident CTAs", G_loc, capacity);
   h->blocks_per_sm = bps;
   if (history) {
     n_groups = B;
     if (G > 1 && (long long)B * G > capacity)
       return fail(PFB200_EINVAL, "pfb200_configure: STORE_HISTORY with %d filters x %d CTAs exceeds the %d co-resident CTAs", B, G, capacity);
   } else {
-    n_groups = capacity / G;
+    n_groups = capacity / G_loc;
     if (n_groups > B) n_groups = B;
     if (h->opt_max_groups > 0 && n_groups > h->opt_max_groups) n_groups = (int)h->opt_max_groups;
     if (n_groups < 1) n_groups = 1;
@@ -360,7 +389,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
+  p.N = N; p.NS = R > 1 ? G_loc * per : (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
+  p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0;
   p.RX = history ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
   p.RA = history ? T + 1 : L + 2;
   p.RW = history ? T + 1 : 3;
@@ -399,8 +429,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->abortf.reserve(16));
   CUDA_TRY(h->stat_m.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->stat_S.reserve((size_t)B * T1 * 8));
-  CUDA_TRY(h->filt_part.reserve((size_t)B * T1 * G * 8));
-  CUDA_TRY(h->smo_part.reserve((size_t)B * T1 * G * (P + 1) * 8));
+  CUDA_TRY(h->filt_part.reserve((size_t)B * T1 * G_loc * 8));
+  CUDA_TRY(h->smo_part.reserve((size_t)B * T1 * G_loc * (P + 1) * 8));
   CUDA_TRY(h->traj_k.reserve((size_t)B * 4));
   CUDA_TRY(h->traj_idx.reserve((size_t)B * 4));
   CUDA_TRY(h->ll_terms.reserve((size_t)B * T1 * 8));
@@ -409,7 +439,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->smo.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->grad.reserve((size_t)B * P * T1 * 8));
   CUDA_TRY(h->traj.reserve((size_t)B * T1 * 8));
-  CUDA_TRY(h->prof.reserve((size_t)n_groups * G * kProfSlots * 8));
+  CUDA_TRY(h->prof.reserve((size_t)n_groups * G_loc * kProfSlots * 8));
 
   p.obs = h->obs.as<double>();
   p.consts = h->consts.as<double>();
@@ -431,6 +461,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.traj_k = h->traj_k.as<int>();
   p.traj_idx = h->traj_idx.as<int>();
   p.prof = h->prof.as<long long>();
+  for (int r = 0; r < 8; ++r) { p.peer_x[r] = p.x_ring; p.peer_lw[r] = p.logw; p.peer_anc[r] = p.anc_ring; p.peer_xval[r] = p.xval; p.peer_xcount[r] = p.xcount; }
 
   // ---- uploads
   CUDA_TRY(cudaMemcpyAsync(h->obs.ptr, obs, n_obs_rows * T1 * 8, cudaMemcpyHostToDevice, h->stream));
@@ -459,10 +490,16 @@ int pfb200_execute(pfb200_handle* h) {
   DeviceProblem& p = h->prob;
   const size_t T1 = (size_t)p.T + 1;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, (size_t)p.n_groups * 32 * 4, h->stream));
+  if (p.R > 1) {
+    if (!h->dist_connected) return fail(PFB200_ESTATE, "pfb200_execute: distributed filter is not connected (pfb200_dist_connect)");
+    p.epoch0 = h->dist_epoch;               // peer counters keep counting across launches
+    h->dist_epoch += 2u * (unsigned)p.T + 3u;  // exchanges per launch: init + 2 per step + 2 at the end
+  } else {
+    CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, (size_t)p.n_groups * 32 * 4, h->stream));
+  }
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
-  const dim3 grid(p.n_groups * p.G), block(kBlock);
+  const dim3 grid(p.n_groups * p.G_loc), block(kBlock);
   {
     // The ancestor ring is re-read every time step for L steps (fixed-lag lineage walks) while
     // particles and log-weights stream through: keep it resident in L2.
@@ -491,7 +528,7 @@ int pfb200_execute(pfb200_handle* h) {
   }
   CUDA_TRY(cudaEventRecord(h->evk1, h->stream));
   FinalizeArgs fa{};
-  fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G; fa.do_smoother = p.do_smoother;
+  fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G_loc; fa.do_smoother = p.do_smoother;
   fa.stat_m = p.stat_m; fa.stat_S = p.stat_S; fa.filt_part = p.filt_part; fa.smo_part = p.smo_part;
   fa.ll_terms = h->ll_terms.as<double>(); fa.log_like = h->log_like.as<double>();
   fa.filt = h->filt.as<double>(); fa.smo = h->smo.as<double>(); fa.grad = h->grad.as<double>();
@@ -629,10 +666,51 @@ int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, in
   return pfb200_fetch(h, log_like, filt, smo, grad_terms, traj_index, traj);
 }
 
+// ---- distributed single filter: exchange of CUDA IPC handles between the per-GPU processes ----
+
+int pfb200_dist_handle_bytes(void) { return 5 * (int)sizeof(cudaIpcMemHandle_t); }
+
+int pfb200_dist_export(pfb200_handle* h, void* out, int bytes) {
+  if (!h || !out || !h->configured) return fail(PFB200_ESTATE, "pfb200_dist_export: configure first");
+  if (h->prob.R < 2) return fail(PFB200_ESTATE, "pfb200_dist_export: set dist_world/dist_rank before configure");
+  if (bytes < pfb200_dist_handle_bytes()) return fail(PFB200_EINVAL, "pfb200_dist_export: buffer too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  dist_close(h);
+  h->dist_connected = false;
+  cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(out);
+  void* ptrs[5] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr};
+  for (int k = 0; k < 5; ++k) CUDA_TRY(cudaIpcGetMemHandle(&hs[k], ptrs[k]));
+  // fresh counters; the caller synchronises all ranks (host barrier) between connect and execute
+  CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
+  h->dist_epoch = 0;
+  return PFB200_OK;
+}
+
+int pfb200_dist_connect(pfb200_handle* h, const void* all_handles, int world) {
+  if (!h || !all_handles || !h->configured) return fail(PFB200_ESTATE, "pfb200_dist_connect: configure first");
+  DeviceProblem& p = h->prob;
+  if (world != p.R) return fail(PFB200_EINVAL, "pfb200_dist_connect: world %d != configured dist_world %d", world, p.R);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+  void* own[5] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr};
+  for (int r = 0; r < world; ++r) {
+    void* ptr[5];
+    for (int k = 0; k < 5; ++k) {
+      if (r == p.rank) { ptr[k] = own[k]; continue; }
+      CUDA_TRY(cudaIpcOpenMemHandle(&ptr[k], hs[r * 5 + k], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_opened[r][k] = ptr[k];
+    }
+    p.peer_x[r] = ptr[0]; p.peer_lw[r] = ptr[1]; p.peer_anc[r] = reinterpret_cast<int*>(ptr[2]);
+    p.peer_xval[r] = reinterpret_cast<double*>(ptr[3]); p.peer_xcount[r] = reinterpret_cast<unsigned*>(ptr[4]);
+  }
+  h->dist_connected = true;
+  return PFB200_OK;
+}
+
 int pfb200_debug_profile(pfb200_handle* h, long long* out, int max_ctas) {
   if (!h || !out || !h->executed) return fail(PFB200_ESTATE, "pfb200_debug_profile: nothing executed yet");
   CUDA_TRY(cudaSetDevice(h->device));
-  int n = h->prob.n_groups * h->prob.G;
+  int n = h->prob.n_groups * h->prob.G_loc;
   if (n > max_ctas) n = max_ctas;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaMemcpy(out, h->prof.ptr, (size_t)n * kProfSlots * 8, cudaMemcpyDeviceToHost));

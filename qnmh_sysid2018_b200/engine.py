@@ -187,6 +187,17 @@ class Engine(object):
         self.execute()
         return self.fetch()
 
+    # ---- one filter sharded over several GPUs (see include/pfb200.h, pfb200_dist_*)
+    def dist_export(self):
+        n = self._lib.pfb200_dist_handle_bytes()
+        buf = C.create_string_buffer(n)
+        L.check(self._lib.pfb200_dist_export(self._h, buf, n))
+        return buf.raw
+
+    def dist_connect(self, all_handles, world):
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        L.check(self._lib.pfb200_dist_connect(self._h, buf, int(world)))
+
     def debug_profile(self, max_ctas=4096):
         """(n_ctas, 12) cycle counters per phase; all zero unless built with -DPFB_PROFILE."""
         buf = np.zeros((max_ctas, 16), dtype=np.int64)
