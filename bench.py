@@ -39,6 +39,8 @@ WORKLOADS = {
     "c3": ("lgss", 4096, 4096, 500),
     "c4": ("sv", 1, 1 << 16, 1000),
     "c1": ("lgss", 1, 1000, 500),
+    # one filter sharded over ALL ranks (peer-memory exchange inside the kernel); B/N/T: whole job
+    "c5": ("lgss", 1, 1 << 24, 100),
 }
 
 
@@ -160,8 +162,9 @@ def _cpu_one(args):
 def cpu_sample_size(model, B, N, T):
     """Bounded sample of the workload: same N, fewer time steps / filters (10-30 s of CPU work)."""
     budget = 2.6e7  # particle-timesteps one NumPy process gets through in roughly 10 s
-    T_s = int(max(2 * FIXED_LAG + 5, min(T, budget // N)))
-    return N, T_s
+    N_s = min(N, 1 << 20)  # the NumPy port keeps (T+1, N) arrays: cap the sample's particle count
+    T_s = int(max(2 * FIXED_LAG + 5, min(T, budget // N_s)))
+    return N_s, T_s
 
 
 def run_cpu_baseline(model, B, N, T, procs=1, reps=1):
@@ -216,6 +219,16 @@ def reference_arm(args):
 
 
 def workload_config(args, model, B, N, T):
+    if getattr(args, "particles_log2", 0):
+        N = 1 << args.particles_log2
+    if args.workload == "c5":
+        return {"workload": "C5: ONE %s filter sharded over all GPUs, N=%d particles x T=%d, L=%d, PF + fixed-lag "
+                            "smoother; children pushed to the owner rank over NVLink peer memory, per-step "
+                            "all-gather of CDF tile totals and max log-weight inside the persistent kernel"
+                            % (model.upper(), N, T, FIXED_LAG),
+                "no_particles": N, "no_obs": T, "fixed_lag": FIXED_LAG,
+                "parallelism": "particles sharded by index range over ranks",
+                "l2": "no flush: rings (%.0f MB per GPU at 1 GPU) exceed L2" % (N * 176 / 1e6)}
     return {"workload": "%s: %s, %d filter(s)/GPU x N=%d particles x T=%d, L=%d, systematic resampling, "
                         "PF + fixed-lag smoother (ll, filtered/smoothed means, score terms)"
                         % (args.workload.upper(), model.upper(), B, N, T, FIXED_LAG),
@@ -257,9 +270,19 @@ def gpu_arm(args):
 
     stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the events share it
     torch.cuda.set_stream(stream)
-    eng = Engine(model, dtype, local_rank)
-    eng.set_stream(stream.cuda_stream)
-    eng.configure(obs, thetas, N, FIXED_LAG, True, True, 0.0, "systematic", seed=SEED, eval_ids=eval_ids)
+    sharded = args.workload == "c5" and world > 1  # ONE filter over all ranks (strong scaling)
+    if args.particles_log2:
+        N = 1 << args.particles_log2
+    if sharded:
+        from qnmh_sysid2018_b200.distributed import DistributedParticleFilter
+        dpf = DistributedParticleFilter(model, dtype, local_rank)
+        eng = dpf.engine
+        eng.set_stream(stream.cuda_stream)
+        dpf.prepare(obs, theta0, N, FIXED_LAG, seed=SEED, eval_id=0)
+    else:
+        eng = Engine(model, dtype, local_rank)
+        eng.set_stream(stream.cuda_stream)
+        eng.configure(obs, thetas, N, FIXED_LAG, True, True, 0.0, "systematic", seed=SEED, eval_ids=eval_ids)
 
     def barrier():
         if world > 1:
@@ -305,6 +328,10 @@ def gpu_arm(args):
             "traj": np.empty((B, T + 1))}
 
     def e2e_step():
+        if sharded:  # inputs are re-uploaded and the peer memory re-connected on every call
+            dpf.prepare(h_obs, theta0, N, FIXED_LAG, seed=SEED, eval_id=0)
+            dpf.execute()
+            return dpf.fetch()
         eng.configure(h_obs, h_theta, N, FIXED_LAG, True, True, 0.0, "systematic", seed=SEED, eval_ids=h_ev)
         eng.execute()
         return eng.fetch(outs)
@@ -325,14 +352,15 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(t[0]), float(t[1])
 
-    units_per_step = world * B * N * T
+    units_per_step = (1 if sharded else world) * B * N * T
     value = units_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = units_per_step * args.steps / e2e_s
 
     if rank == 0:
         bytes_unit = algorithmic_bytes_per_particle_step(args.dtype, FIXED_LAG)
         peak, peak_src = measured_peak_gbs()
-        achieved = bytes_unit * B * N * T / (kernel_ms * 1e-3) / 1e9
+        per_gpu_units = B * N * T / (world if sharded else 1)
+        achieved = bytes_unit * per_gpu_units / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -345,7 +373,8 @@ def gpu_arm(args):
         line = {
             "metric": "particle-timesteps/sec (PF+fixed-lag smoother)", "value": value,
             "unit": "particle-timesteps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, model, B, N, T),
             "clocks": clocks,
@@ -356,7 +385,7 @@ def gpu_arm(args):
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pf_persistent_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_particle_step": bytes_unit,
-                         "algorithmic_bytes_per_launch": bytes_unit * B * N * T,
+                         "algorithmic_bytes_per_launch": bytes_unit * per_gpu_units,
                          "peak_source": peak_src},
             "geometry": {"ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
                          "block_threads": eng.info("block_threads"), "cooperative": eng.info("cooperative")},
@@ -379,6 +408,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--particles-log2", type=int, default=0, help="override N = 2^k (c5 sweep)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

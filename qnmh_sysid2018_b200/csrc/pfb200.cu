@@ -334,7 +334,6 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   // ---- launch geometry
   const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
   const size_t smem_limit = 200 * 1024;  // dynamic shared memory we are willing to use per CTA
-  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
   const int R = (int)h->opt_dist_world, rank = (int)h->opt_dist_rank;
   if (R > 1) {
     if (rank < 0 || rank >= R) return fail(PFB200_EINVAL, "pfb200_configure: dist_rank %d out of range for dist_world %d", rank, R);
@@ -343,6 +342,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     h->kernel = h->kernel_general;  // the peer-memory paths live in the general flavour
   }
   h->dist_connected = false;
+  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
   int G = 1, G_loc = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0;
   size_t smem = 0;
   for (int pass = 0; pass < 3; ++pass) {

@@ -119,7 +119,8 @@ def test_dropin_estimator_matches_reference_results(name):
 # ragged tails, N not a multiple of anything, N < block size, fixed lag > T
 GEOMETRIES = [(1, 20, 3, 0), (2, 20, 3, 0), (37, 25, 4, 1), (1000, 40, 10, 1), (3584, 30, 5, 1),
               (3585, 30, 5, 1), (5001, 30, 6, 1), (9000, 25, 5, 1), (5001, 30, 6, 3), (20000, 30, 10, 0),
-              (65536, 20, 10, 0), (70001, 15, 4, 9), (300, 12, 30, 2), (100000, 12, 3, 5)]
+              (65536, 20, 10, 0), (70001, 15, 4, 9), (300, 12, 30, 2), (100000, 12, 3, 5),
+              (100000, 10, 3, 1), (70001, 12, 4, 2)]  # the last two stream > 8 sub-chunks per CTA
 
 
 @pytest.mark.parametrize("N,T,L,G", GEOMETRIES)
