@@ -73,6 +73,86 @@ template <typename Real>
 __device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t eval_id, uint32_t t,
                                                    uint32_t pair, Real& z_even, Real& z_odd);
 
+// ---- fp64 Box-Muller building blocks.  The general-purpose log / sqrt / sincospi of the CUDA math
+// library cost ~180 instructions per normal pair (argument classes that cannot occur here: huge,
+// denormal, negative, non-finite).  These versions only cover the ranges Box-Muller produces and
+// stay within a few ulp (checked against NumPy in tests/test_gpu_parity.py).
+
+// ln(u) for u in [2^-53, 1]: fdlibm's scheme -- u = 2^e m, m in [sqrt(1/2), sqrt(2)), f = m - 1,
+// s = f / (2 + f), ln(1+f) = f - (f^2/2 - s (f^2/2 + R(s^2))).  The quotient uses a float-seeded
+// reciprocal refined by two Newton steps and one residual correction.
+__device__ __forceinline__ double log_unit_interval(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, lo);  // [1, 2)
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double f = m - 1.0;
+  const double d = 2.0 + f;
+  double r = (double)__frcp_rn((float)d);
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  double sq = f * r;
+  sq = fma(fma(-d, sq, f), r, sq);
+  const double z = sq * sq;
+  double R = 1.479819860511658591e-01;
+  R = fma(R, z, 1.531383769920937332e-01);
+  R = fma(R, z, 1.818357216161805012e-01);
+  R = fma(R, z, 2.222219843214978396e-01);
+  R = fma(R, z, 2.857142874366239149e-01);
+  R = fma(R, z, 3.999999999940941908e-01);
+  R = fma(R, z, 6.666666666666735130e-01);
+  R *= z;
+  const double hfsq = 0.5 * f * f;
+  const double ef = (double)e;
+  return ef * 6.93147180369123816490e-01 - ((hfsq - (sq * (hfsq + R) + ef * 1.90821492927058770002e-10)) - f);
+}
+
+// sqrt(x) for 0 <= x < 2^100: float-seeded reciprocal square root, two Newton steps, one correction
+__device__ __forceinline__ double sqrt_nonneg(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  double r = x * y;
+  r = fma(fma(-r, r, x), 0.5 * y, r);
+  return x > 0.0 ? r : 0.0;
+}
+
+// sin(pi a), cos(pi a) for a in [0, 2): quadrant reduction a = k/2 + r, |r| <= 1/4, Taylor
+// polynomials in (pi r) (truncation < 5e-17)
+__device__ __forceinline__ void sincospi_0_2(double a, double& sn, double& cs) {
+  const double kf = rint(2.0 * a);
+  const int k = (int)kf;
+  const double r = fma(kf, -0.5, a);
+  const double r2 = r * r;
+  double ps = 7.95205400147550838e-07;
+  ps = fma(ps, r2, -2.19153534478302037e-05);
+  ps = fma(ps, r2, 4.66302805767612337e-04);
+  ps = fma(ps, r2, -7.37043094571434784e-03);
+  ps = fma(ps, r2, 8.21458866111281910e-02);
+  ps = fma(ps, r2, -5.99264529320791883e-01);
+  ps = fma(ps, r2, 2.55016403987734508e+00);
+  ps = fma(ps, r2, -5.16771278004996937e+00);
+  ps = fma(ps, r2, 3.14159265358979312e+00);
+  ps *= r;
+  double pc = -1.38789524622137608e-07;
+  pc = fma(pc, r2, 4.30306958703294391e-06);
+  pc = fma(pc, r2, -1.04638104924845650e-04);
+  pc = fma(pc, r2, 1.92957430940392206e-03);
+  pc = fma(pc, r2, -2.58068913900140508e-02);
+  pc = fma(pc, r2, 2.35330630358893123e-01);
+  pc = fma(pc, r2, -1.33526276885458928e+00);
+  pc = fma(pc, r2, 4.05871212641676760e+00);
+  pc = fma(pc, r2, -4.93480220054467900e+00);
+  pc = fma(pc, r2, 1.0);
+  const bool swap = k & 1;
+  const double s0 = swap ? pc : ps, c0 = swap ? ps : pc;
+  sn = (k & 2) ? -s0 : s0;
+  cs = (((k + 1) & 2) != 0) ? -c0 : c0;
+}
+
 template <>
 __device__ __forceinline__ void philox_normal_pair<double>(uint64_t seed, uint64_t eval_id, uint32_t t,
                                                            uint32_t pair, double& z_even, double& z_odd) {
@@ -80,9 +160,9 @@ __device__ __forceinline__ void philox_normal_pair<double>(uint64_t seed, uint64
   philox4x32_10(seed, eval_id, kStreamZ, t, pair, r);
   const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
   const double u2 = u01_53(r[2], r[3]);
-  const double rad = sqrt(-2.0 * log(u1));
+  const double rad = sqrt_nonneg(-2.0 * log_unit_interval(u1));
   double s, c;
-  sincospi(2.0 * u2, &s, &c);
+  sincospi_0_2(2.0 * u2, s, c);
   z_even = rad * c;
   z_odd = rad * s;
 }
@@ -237,27 +317,24 @@ struct ModelOps<MODEL, float> {
 // exponent bits.  Results below 2^-1021 (weights 1e-307 times the maximum) flush to zero; NaN
 // propagates.  About 1 ulp, ~4x fewer instructions than the general-purpose exp().
 // ------------------------------------------------------------------------------------------
+// Taylor coefficients 1/13! ... 1/0! in constant memory: DFMA takes them as constant-bank operands
+// (a 64-bit immediate would cost two extra instructions per Horner step).
+__constant__ double kExpCoef[14] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.3888888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
+__constant__ double kExpLn2[3] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+
 __device__ __forceinline__ double exp_nonpos(double x) {
-  const double t = x * 1.4426950408889634074;
+  const double t = x * kExpLn2[0];
   if (!(t > -1021.0)) return (t == t) ? 0.0 : t;  // underflow -> 0, NaN -> NaN
   const int k = __double2int_rn(t);
   const double kf = (double)k;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double q = 1.6059043836821613e-10;           // 1/13!
-  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
-  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
-  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
-  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
-  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
-  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
-  q = fma(q, r, 1.3888888888888889e-03);       // 1/6!
-  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
-  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
-  q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  q = fma(q, r, 1.0);
+  double r = fma(kf, kExpLn2[1], x);
+  r = fma(kf, kExpLn2[2], r);
+  double q = kExpCoef[0];
+#pragma unroll
+  for (int i = 1; i < 14; ++i) q = fma(q, r, kExpCoef[i]);
   return q * __hiloint2double((k + 1023) << 20, 0);
 }
 

@@ -34,6 +34,9 @@ namespace pfb200 {
 #define PFB_TICK(slot) do { } while (0)
 #endif
 constexpr int kProfSlots = 16;
+#ifndef PFB_SMOOTH_BATCH
+#define PFB_SMOOTH_BATCH 0  // lineages per thread in flight in the smoother job (0 = ITEMS)
+#endif
 #ifndef PFB_SMOOTH_SPLIT
 #define PFB_SMOOTH_SPLIT 1  // 1: half of the deferred smoother job per exchange wait; 0: all of it behind exchange 1
 #endif
@@ -410,10 +413,11 @@ struct PfKernel {
                              const double* obs, int tau, int j_begin, int j_end, int c_lo, int c_hi,
                              double (&acc)[kMaxParams + 1]) {
     const Real* lw = lwr + (size_t)(tau % p.RW) * p.NS;
-    for (int c = c_lo; c < c_hi; ++c) {
-      const int c0 = j_begin + c * kChunk;
-      smooth_chunk<ITEMS>(lw, m_tau, xr, ar, obs, tau, tau - p.L, c0, min(kChunk, j_end - c0), acc);
-    }
+    constexpr int SB = (PFB_SMOOTH_BATCH > 0 && PFB_SMOOTH_BATCH < ITEMS) ? PFB_SMOOTH_BATCH : ITEMS;
+    const int first = j_begin + c_lo * kChunk;
+    const int last = min(j_end, j_begin + c_hi * kChunk);
+    for (int c0 = first; c0 < last; c0 += SB * BLOCK)
+      smooth_chunk<SB>(lw, m_tau, xr, ar, obs, tau, tau - p.L, c0, min(SB * BLOCK, last - c0), acc);
   }
 
   __device__ void write_smooth_partials(int b, int i, double (&acc)[kMaxParams + 1]) {
@@ -510,10 +514,6 @@ struct PfKernel {
       Real xp[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) xp[e] = ld_cg(x_prev + c0 + j[e]);
-#ifdef PFB_PROFILE
-      if (xp[0] == (Real)123456.789) mx = 0.0;  // force the gathers to complete here
-      PFB_TICK(12);
-#endif
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
         Real z0, z1;

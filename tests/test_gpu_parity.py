@@ -219,6 +219,22 @@ def test_philox_path_replayed_through_oracle():
     np.testing.assert_allclose(out["grad_terms"][0], ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
 
 
+def test_device_normals_match_numpy_box_muller():
+    """The device's Philox4x32-10 stream and its custom fp64 log / sqrt / sincospi against a NumPy
+    restatement: same bits in, normals equal to a few ulp; moments and tails as expected."""
+    import philox_ref
+    eng = _engine("lgss")
+    for seed, ev, t in ((1234, 5, 1), (87655678, 0, 0), (2 ** 40 + 17, 2 ** 33 + 1, 999)):
+        n = 200001
+        z = eng.philox_normals(seed, ev, t, n)
+        ref = philox_ref.normals(seed, ev, t, n)
+        np.testing.assert_allclose(z, ref, rtol=0, atol=5e-15)
+        assert abs(eng.philox_uniforms(seed, ev, max(t, 1))[0] - philox_ref.uniform(seed, ev, 1, max(t, 1))) == 0.0
+    z = eng.philox_normals(7, 7, 3, 2000000)
+    assert abs(z.mean()) < 3e-3 and abs(z.std() - 1) < 2e-3
+    assert abs(np.mean(z ** 4) - 3.0) < 0.03 and np.abs(z).max() > 4.5
+
+
 def test_philox_loglik_is_consistent_with_kalman():
     """Statistical check without injected noise: the PF log-likelihood on the reference
     data at N=2^16 is within Monte Carlo error of the reference Kalman log-likelihood."""
