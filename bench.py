@@ -380,7 +380,7 @@ def gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": eng.info("kernel_launches_per_execute") * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pf_persistent_kernel", "kernel_ms": kernel_ms,

@@ -849,47 +849,53 @@ struct FinalizeArgs {
   double* grad;       // [B][P][T+1]
 };
 
+// grid = (B, ceil((T+1)/256)): one thread per (filter, time step)
 __global__ void __launch_bounds__(256) pf_finalize_kernel(const FinalizeArgs a) {
   const int b = blockIdx.x;
   const int T1 = a.T + 1;
-  __shared__ double sh[256];
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (t >= T1) return;
   const double logN = log((double)a.N);
-  double ll_acc = 0.0;
-  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
-    const size_t bt = (size_t)b * T1 + t;
-    const double S = a.stat_S[bt];
-    double f = 0.0;
-    for (int g = 0; g < a.G; ++g) f += a.filt_part[bt * a.G + g];
-    const double filt = (t == 0) ? 0.0 : f / S;
-    double ll = 0.0;
-    if (t > 0) { ll = a.stat_m[bt]; ll += log(S); ll -= logN; }
-    a.ll_terms[bt] = ll;
-    a.filt[bt] = filt;
-    ll_acc += ll;
-    if (a.do_smoother) {
-      if (t < a.T) {
-        const int lag = min(t + a.L, a.T);
-        const double Sl = a.stat_S[(size_t)b * T1 + lag];
-        for (int k = 0; k <= a.P; ++k) {
-          double s = 0.0;
-          for (int g = 0; g < a.G; ++g) s += a.smo_part[(bt * a.G + g) * (a.P + 1) + k];
-          s /= Sl;
-          if (k == 0) a.smo[bt] = s;
-          else a.grad[((size_t)b * a.P + (k - 1)) * T1 + t] = s;
-        }
-      } else {
-        a.smo[bt] = filt;
-        for (int k = 0; k < a.P; ++k) a.grad[((size_t)b * a.P + k) * T1 + t] = 0.0;
+  const size_t bt = (size_t)b * T1 + t;
+  const double S = a.stat_S[bt];
+  double f = 0.0;
+  for (int g = 0; g < a.G; ++g) f += a.filt_part[bt * a.G + g];
+  const double filt = (t == 0) ? 0.0 : f / S;
+  double ll = 0.0;
+  if (t > 0) { ll = a.stat_m[bt]; ll += log(S); ll -= logN; }
+  a.ll_terms[bt] = ll;
+  a.filt[bt] = filt;
+  if (a.do_smoother) {
+    if (t < a.T) {
+      const int lag = min(t + a.L, a.T);
+      const double Sl = a.stat_S[(size_t)b * T1 + lag];
+      for (int k = 0; k <= a.P; ++k) {
+        double s = 0.0;
+        for (int g = 0; g < a.G; ++g) s += a.smo_part[(bt * a.G + g) * (a.P + 1) + k];
+        s /= Sl;
+        if (k == 0) a.smo[bt] = s;
+        else a.grad[((size_t)b * a.P + (k - 1)) * T1 + t] = s;
       }
+    } else {
+      a.smo[bt] = filt;
+      for (int k = 0; k < a.P; ++k) a.grad[((size_t)b * a.P + k) * T1 + t] = 0.0;
     }
   }
-  sh[threadIdx.x] = ll_acc;
+}
+
+// log_like[b] = sum_t ll_terms[b][t] in a fixed order (standard.py:110); one block per filter
+__global__ void __launch_bounds__(256) pf_loglike_kernel(const double* ll_terms, double* log_like, int T1) {
+  const int b = blockIdx.x;
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) acc += ll_terms[(size_t)b * T1 + t];
+  sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) a.log_like[b] = sh[0];
+  if (threadIdx.x == 0) log_like[b] = sh[0];
 }
 
 // trajectory rows from the stored history: traj[b][t] = x[b][t][traj_idx[b]]

@@ -281,7 +281,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "blocks_per_sm")) *value = h->blocks_per_sm;
   else if (!strcmp(name, "cooperative")) *value = h->cooperative ? 1 : 0;
   else if (!strcmp(name, "smem_bytes")) *value = (long long)h->smem_bytes;
-  else if (!strcmp(name, "kernel_launches_per_execute")) *value = 2 + ((h->flags & PFB200_FLAG_STORE_HISTORY) ? 1 : 0);
+  else if (!strcmp(name, "kernel_launches_per_execute")) *value = 3 + ((h->flags & PFB200_FLAG_STORE_HISTORY) ? 1 : 0);
   else if (!strcmp(name, "workspace_bytes")) {
     *value = (long long)(h->x_ring.cap + h->logw.cap + h->anc.cap + h->filt_part.cap + h->smo_part.cap);
   } else return fail(PFB200_EINVAL, "pfb200_get_info: unknown key '%s'", name);
@@ -532,7 +532,9 @@ int pfb200_execute(pfb200_handle* h) {
   fa.stat_m = p.stat_m; fa.stat_S = p.stat_S; fa.filt_part = p.filt_part; fa.smo_part = p.smo_part;
   fa.ll_terms = h->ll_terms.as<double>(); fa.log_like = h->log_like.as<double>();
   fa.filt = h->filt.as<double>(); fa.smo = h->smo.as<double>(); fa.grad = h->grad.as<double>();
-  pf_finalize_kernel<<<p.B, 256, 0, h->stream>>>(fa);
+  pf_finalize_kernel<<<dim3((unsigned)p.B, (unsigned)((T1 + 255) / 256)), 256, 0, h->stream>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  pf_loglike_kernel<<<p.B, 256, 0, h->stream>>>(fa.ll_terms, fa.log_like, (int)T1);
   CUDA_TRY(cudaGetLastError());
   if (h->flags & PFB200_FLAG_STORE_HISTORY) {
     if (h->dtype == PFB200_F64)
