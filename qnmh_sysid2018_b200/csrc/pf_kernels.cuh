@@ -453,32 +453,39 @@ struct PfKernel {
     return n;
   }
 
-  // #{ jl in [0, len) : tile[jl] <= pos }  -- branch-free power-of-two descent; `top` is the
-  // largest power of two <= len; `ta` = shared-window address of tile[-1]
-  __device__ __forceinline__ int upper_bound_tile(uint32_t ta, double pos, int len, int top) const {
+  // #{ jl in [0, len) : tile[jl] <= pos }  -- power-of-two descent written as straight-line code:
+  // the probe index is clamped to len instead of predicating the load, and the loop is fully
+  // unrolled from a compile-time first step, so the whole search is one basic block that the
+  // compiler interleaves with the (independent) Philox / Box-Muller chains of the same quad.
+  // Steps larger than len only re-probe the last element.  `ta` = shared-window address of tile[-1].
+  template <int TOP>
+  __device__ __forceinline__ int upper_bound_unrolled(uint32_t ta, double pos, int len) const {
     int lo = 0;
-    for (int step = top; step > 0; step >>= 1) {
-      const int probe = lo + step;
-      if (probe <= len && lds_f64(ta + 8u * probe) <= pos) lo = probe;
+#pragma unroll
+    for (int step = TOP; step > 0; step >>= 1) {
+      const int probe = min(lo + step, len);
+      lo = (lds_f64(ta + 8u * probe) <= pos) ? probe : lo;
     }
     return lo;
   }
+  __device__ __forceinline__ int upper_bound_tile(uint32_t ta, double pos, int len, int top) const {
+    if (top <= 512) return upper_bound_unrolled<512>(ta, pos, len);    // tiles of up to 1023 parents
+    if (top <= 4096) return upper_bound_unrolled<4096>(ta, pos, len);  // up to 8191
+    return upper_bound_unrolled<16384>(ta, pos, len);                  // up to 32767 (tile_cap <= 28672)
+  }
 
-  // parent (tile-local) of a child at `pos`, knowing that it is >= lo (children are monotone):
-  // branch-free 3-step descent inside the window [lo, lo+8); the full descent only when the
-  // answer lies beyond the window (several consecutive parents without offspring)
+  // count of tile elements <= pos, knowing that it is >= lo (children are monotone): the next 4
+  // elements are probed at once (independent loads); the full descent only when the answer lies
+  // beyond them (four consecutive parents without offspring)
   __device__ __forceinline__ int next_parent(uint32_t ta, double pos, int lo, int len, int top) const {
-    const int wend = min(lo + 8, len);
-    if (lds_f64(ta + 8u * wend) <= pos) {  // not inside the window
-      return (wend == len) ? len : upper_bound_tile(ta, pos, len, top);
-    }
-    int r = lo;
+    int cnt = 0;
 #pragma unroll
-    for (int step = 4; step > 0; step >>= 1) {
-      const int probe = r + step;
-      if (probe <= wend && lds_f64(ta + 8u * probe) <= pos) r = probe;
+    for (int k = 1; k <= 4; ++k) {
+      const double v = lds_f64(ta + 8u * min(lo + k, len));
+      cnt += (lo + k <= len && v <= pos) ? 1 : 0;
     }
-    return r;
+    if (cnt == 4 && lo + 4 < len) return upper_bound_tile(ta, pos, len, top);
+    return lo + cnt;
   }
 
   // ---- children of the normalised CDF tile: resample + propagate + weight (phase B).  A thread
@@ -506,8 +513,7 @@ struct PfKernel {
         if (full || (n >= n_lo && n < n_hi)) {
           const double pos = position(n, u, t, inj_u_t, eval_id);
           lo = (lo < 0) ? upper_bound_tile(ta, pos, len, top) : next_parent(ta, pos, lo, len, top);
-          if (lo > len - 1) lo = len - 1;
-          j[e] = lo;
+          j[e] = min(lo, len - 1);
         }
       }
       PFB_TICK(11);
