@@ -112,6 +112,10 @@ class ParticleMethodsB200(object):
     def _evaluate(self, model, do_smoother):
         s = self.settings
         kind = model_kind_of(model)
+        if s['resampling_method'] == 'multinomial':
+            raise NotImplementedError("multinomial resampling (resampling.pyx:33-42) has no device path yet: its "
+                                      "ancestors are not monotone, which the push-style resampling kernel "
+                                      "relies on; use 'systematic' (all reference scripts) or 'stratified'")
         if s['resampling_method'] not in ('systematic', 'stratified'):
             raise ValueError("Unknown resampling method selected...")
         engine = self._get_engine(kind)

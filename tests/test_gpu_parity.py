@@ -235,6 +235,27 @@ def test_device_normals_match_numpy_box_muller():
     assert abs(np.mean(z ** 4) - 3.0) < 0.03 and np.abs(z).max() > 4.5
 
 
+def test_filtered_means_and_loglik_against_exact_kalman():
+    """At N = 2^18 the PF's filtered means and log-likelihood must sit on the exact Kalman values
+    (stationary initial law on both sides): |filt - KF| is a few Monte Carlo standard errors."""
+    from oracle import kalman_oracle as ko
+    rng = np.random.default_rng(8)
+    theta = np.array([0.2, 0.5, 1.0, 0.5])
+    obs = _synthetic_obs("lgss", theta, 200, rng)
+    m0, p0 = ko.stationary_prior(theta)
+    # the PF draws x_0 from the stationary law and then propagates: start the KF one step earlier
+    kf = ko.kalman_filter(obs, theta, initial_state=m0, initial_cov=p0)
+    eng = _engine("lgss")
+    out = eng.run(obs, theta, 1 << 18, 10, True, True, 0.0, "systematic", seed=21)
+    err = np.abs(out["filt"][0][1:] - kf["filt_state_est"][1:])
+    assert err.max() < 6.0 * np.sqrt(kf["filt_state_cov"][1:].max() / (1 << 18)) * 3, err.max()
+    assert abs(out["log_like"][0] - kf["log_like"]) < 0.15, (out["log_like"][0], kf["log_like"])
+    for dtype in ("float32",):
+        o32 = _engine("lgss", dtype).run(obs, theta, 1 << 18, 10, True, True, 0.0, "systematic", seed=21)
+        assert abs(o32["log_like"][0] - kf["log_like"]) < 0.3  # documented fp32 bound: ~1e-3 relative
+        assert np.abs(o32["filt"][0][1:] - kf["filt_state_est"][1:]).max() < 0.02
+
+
 def test_philox_loglik_is_consistent_with_kalman():
     """Statistical check without injected noise: the PF log-likelihood on the reference
     data at N=2^16 is within Monte Carlo error of the reference Kalman log-likelihood."""
