@@ -45,6 +45,10 @@ extern "C" {
 #define PFB200_MODEL_LGSS 0 /* models/linear_gaussian_model.py:            theta = mu, phi, sigma_v, sigma_e */
 #define PFB200_MODEL_SV 1   /* models/stochastic_volatility_model.py:      theta = mu, phi, sigma_v          */
 #define PFB200_MODEL_SVL 2  /* models/stochastic_volatility_model_leverage.py: theta = mu, phi, sigma_v, rho */
+#define PFB200_MODEL_LGSS_FA 3 /* LGSS with the FULLY ADAPTED (optimal proposal) auxiliary particle filter: not in the
+                                  reference, named by the north star; same theta as LGSS.  filt = equally
+                                  weighted means, log_like = sum_t log mean_n p(y_t | x_{t-1}[n]); the smoother weights
+                                  of lag time tau are the look-ahead weights p(y_{tau+1} | x_tau) */
 
 /* dtype: storage / per-particle arithmetic type (CDF, reductions and outputs are always fp64) */
 #define PFB200_F64 0

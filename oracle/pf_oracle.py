@@ -348,6 +348,54 @@ def estimate_gradient_and_hessian(score, hess, param_names, params_to_estimate,
                 log_joint_gradient_estimate=score, log_joint_hessian_estimate=hess)
 
 
+# ----------------------------------------------------------------------------------------------
+# fully adapted auxiliary particle filter for the LGSS model.  NOT in the reference (only
+# the bootstrap filter exists, standard.py:43); the north star names it.  Parity status of this
+# function: UNPINNED by reference vectors -- it is pinned instead to the exact Kalman log-likelihood
+# (tests) and shares resampling / smoother code with the pinned bootstrap path above.
+#   resampling weights of generation t:  v_t[n] = p(y_{t+1} | x_t[n]) = N(y_{t+1}; mu+phi(x-mu), sv^2+se^2)
+#   proposal:  x_{t+1} ~ p(x_{t+1} | x_t, y_{t+1}) = N(A pred + B y_{t+1}, s^2),
+#              A = se^2/(sv^2+se^2), B = sv^2/(sv^2+se^2), s^2 = sv^2 se^2/(sv^2+se^2)
+#   log_like = sum_t log( mean_n v_{t-1}[n] );  filtered mean = plain average (equal weights)
+# ----------------------------------------------------------------------------------------------
+def fully_adapted_filter(theta, obs, no_particles, draws, initial_state_value=0.0,
+                         generate_initial_state=True):
+    theta = np.asarray(theta, dtype=np.float64)
+    obs = np.asarray(obs, dtype=np.float64).reshape(-1)
+    mu, phi, sv, se = theta
+    T1, N = obs.shape[0], int(no_particles)
+    tot = sv * sv + se * se
+    A, Bc, s_prop, s_pred = se * se / tot, sv * sv / tot, np.sqrt(sv * sv * se * se / tot), np.sqrt(tot)
+    x = np.zeros((T1, N))
+    w = np.zeros((T1, N))
+    anc = np.zeros((T1, N), dtype=np.int32)
+    filt = np.zeros((T1, 1))
+    ll = np.zeros(T1)
+    x[0] = initial_state(MODEL_LGSS, theta, draws.z0) if generate_initial_state else initial_state_value
+    for t in range(0, T1):
+        if t > 0:
+            a = systematic(w[t - 1], draws.u[t])
+            anc[t] = a
+            pred = mu + phi * (x[t - 1, a] - mu)
+            x[t] = (A * pred + Bc * obs[t]) + s_prop * draws.z[t]
+            filt[t] = np.sum(x[t]) / N
+        if t < T1 - 1:  # look-ahead weights
+            logv = _norm_logpdf(obs[t + 1], mu + phi * (x[t] - mu), s_pred)
+            m = np.max(logv)
+            sh = np.exp(logv - m)
+            S = np.sum(sh)
+            w[t] = sh / S
+            ll[t + 1] = m + np.log(S) - np.log(N)
+        else:
+            w[t] = 1.0 / N
+    cdf = np.cumsum(w[T1 - 1])
+    cdf = cdf / cdf[-1]
+    k = int(np.searchsorted(cdf, draws.u_final, side="right"))
+    idx = int(anc[T1 - 1, min(k, N - 1)])
+    return dict(particles=x, weights=w, ancestors=anc, log_like=float(np.sum(ll)), log_like_terms=ll,
+                filt_state_est=filt, state_trajectory=x[:, idx].reshape(1, T1).copy(), trajectory_index=idx)
+
+
 def smoother(model_id, theta, obs, no_particles, fixed_lag, draws, **filter_kwargs):
     """filter + fixed-lag smoother in one call (what `ParticleMethods.smoother` does)."""
     estimate_gradient = filter_kwargs.pop("estimate_gradient", True)

@@ -8,6 +8,7 @@
 //   models/stochastic_volatility_model_leverage.py:77-108,143-156,212-259 (SV with leverage)
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace pfb200 {
@@ -15,13 +16,21 @@ namespace pfb200 {
 constexpr int kMaxParams = 4;
 constexpr int kNumConsts = 16;
 constexpr int kModelLGSS = 0, kModelSV = 1, kModelSVL = 2;
+// Fully adapted (optimal-proposal) auxiliary particle filter for the LGSS model: resampling weights
+// p(y_{t+1} | x_t), proposal p(x_{t+1} | x_t, y_{t+1}).  Not in the reference; named by the
+// north star; pinned to the Kalman log-likelihood and to oracle/pf_oracle.py:fully_adapted_filter.
+constexpr int kModelLGSSFA = 3;
+__host__ __device__ constexpr bool is_fully_adapted(int model) { return model == kModelLGSSFA; }
 
 // Derived per-filter constants, computed on the host with the reference's own expressions
 // (so that e.g. sigma_v**(-2) has the bits Python gives it) -- see host_consts() in pfb200.cu.
 enum ConstIdx {
   C_MU = 0, C_PHI, C_SIGV, C_SIGE_OR_RHO, C_SD0, C_LOGSIGE, C_Q, C_R, C_1MPHI, C_1MPHI2,
-  C_SVRHO, C_STDEV, C_RHOTERM, C_RHOINV_RHO, C_UNUSED0, C_UNUSED1
+  C_SVRHO, C_STDEV, C_RHOTERM, C_RHOINV_RHO, C_FA_A, C_FA_B
 };
+// fully adapted LGSS reuses: C_STDEV = sqrt(sv^2 se^2 / (sv^2+se^2)) (proposal std), C_FA_A = se^2/(sv^2+se^2),
+// C_FA_B = sv^2/(sv^2+se^2) (proposal mean = A*pred + B*y), C_SVRHO = sqrt(sv^2+se^2) (predictive std),
+// C_RHOTERM = log(sqrt(sv^2+se^2))
 
 #define PFB_NORM_LOGC 0.91893853320467267  // log(sqrt(2 pi)), scipy _norm_pdf_logC
 
@@ -221,6 +230,13 @@ __device__ __forceinline__ void load_step_consts(uint32_t c_addr, double (&c)[kN
     c[C_SIGE_OR_RHO] = lds_f64(c_addr + 8 * C_SIGE_OR_RHO);
     c[C_LOGSIGE] = lds_f64(c_addr + 8 * C_LOGSIGE);
   }
+  if (MODEL == kModelLGSSFA) {
+    c[C_STDEV] = lds_f64(c_addr + 8 * C_STDEV);
+    c[C_FA_A] = lds_f64(c_addr + 8 * C_FA_A);
+    c[C_FA_B] = lds_f64(c_addr + 8 * C_FA_B);
+    c[C_SVRHO] = lds_f64(c_addr + 8 * C_SVRHO);
+    c[C_RHOTERM] = lds_f64(c_addr + 8 * C_RHOTERM);
+  }
 }
 
 template <int MODEL>
@@ -232,6 +248,10 @@ struct ModelOps<MODEL, double> {
   // generate_state; y is the observation the model reads for the leverage term
   static __device__ __forceinline__ double propagate(const double* c, double x, double z, double y) {
     double mean = __dadd_rn(c[C_MU], __dmul_rn(c[C_PHI], __dsub_rn(x, c[C_MU])));
+    if (MODEL == kModelLGSSFA) {  // x' ~ p(x' | x, y) = N(A pred + B y, s^2)
+      const double pm = __dadd_rn(__dmul_rn(c[C_FA_A], mean), __dmul_rn(c[C_FA_B], y));
+      return __dadd_rn(pm, __dmul_rn(c[C_STDEV], z));
+    }
     if (MODEL == kModelSVL) {
       const double lev = __dmul_rn(__dmul_rn(c[C_SVRHO], exp(__dmul_rn(-0.5, x))), y);
       mean = __dadd_rn(mean, lev);
@@ -244,6 +264,10 @@ struct ModelOps<MODEL, double> {
     if (MODEL == kModelLGSS) {
       const double zz = __ddiv_rn(__dsub_rn(y, x), c[C_SIGE_OR_RHO]);
       return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), c[C_LOGSIGE]);
+    } else if (MODEL == kModelLGSSFA) {  // log p(y_next | x) = N(y; mu + phi (x - mu), sv^2 + se^2)
+      const double pred = __dadd_rn(c[C_MU], __dmul_rn(c[C_PHI], __dsub_rn(x, c[C_MU])));
+      const double zz = __ddiv_rn(__dsub_rn(y, pred), c[C_SVRHO]);
+      return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), c[C_RHOTERM]);
     } else {
       const double vol = exp(__dmul_rn(0.5, x));
       const double zz = __ddiv_rn(y, vol);
@@ -264,7 +288,7 @@ struct ModelOps<MODEL, double> {
     out[0] = Q * q * c[C_1MPHI];
     out[1] = Q * q * (xc - c[C_MU]) * c[C_1MPHI2];
     out[2] = Q * (q * q) - 1.0;
-    if (MODEL == kModelLGSS) {
+    if (MODEL == kModelLGSS || MODEL == kModelLGSSFA) {
       const double oq = y - xc;
       out[3] = c[C_R] * (oq * oq) - 1.0;
     } else if (MODEL == kModelSVL) {
@@ -288,6 +312,7 @@ struct ModelOps<MODEL, float> {
   static __device__ __forceinline__ float propagate(const double* c, float x, float z, double y) {
     const float mu = (float)c[C_MU];
     float mean = mu + (float)c[C_PHI] * (x - mu);
+    if (MODEL == kModelLGSSFA) return (float)c[C_FA_A] * mean + (float)c[C_FA_B] * (float)y + (float)c[C_STDEV] * z;
     if (MODEL == kModelSVL) {
       mean += (float)c[C_SVRHO] * __expf(-0.5f * x) * (float)y;
       return mean + (float)c[C_STDEV] * z;
@@ -298,6 +323,10 @@ struct ModelOps<MODEL, float> {
     if (MODEL == kModelLGSS) {
       const float zz = ((float)y - x) * (float)(1.0 / c[C_SIGE_OR_RHO]);
       return -0.5f * zz * zz - (float)PFB_NORM_LOGC - (float)c[C_LOGSIGE];
+    } else if (MODEL == kModelLGSSFA) {
+      const float mu = (float)c[C_MU];
+      const float zz = ((float)y - (mu + (float)c[C_PHI] * (x - mu))) * (float)(1.0 / c[C_SVRHO]);
+      return -0.5f * zz * zz - (float)PFB_NORM_LOGC - (float)c[C_RHOTERM];
     } else {
       // -0.5 y^2 exp(-x) - logC - x/2   (log(exp(x/2)) folded analytically in fp32)
       const float yy = (float)y;

@@ -97,6 +97,7 @@ struct PfKernel {
                                                 // thread-blocked smem pass is bank-conflict free)
   static constexpr int kWarps = BLOCK / 32;
   static constexpr int kRedK = kMaxParams + 2;
+  static constexpr bool kFA = is_fully_adapted(MODEL);  // weights of generation t look ahead to y_{t+1}
 
   const DeviceProblem& p;
   double* sh_s;    // [tile_cap] CDF tile
@@ -306,7 +307,7 @@ struct PfKernel {
     for (int k = 0; k < ITEMS; ++k) {
       const int jl = k * BLOCK + tid;
       const double s = (jl < len) ? shifted_weight<Real>(l[k], m) : 0.0;
-      if (accF) f += s * (double)xv[k];
+      if (accF) f += (kFA ? ((jl < len) ? 1.0 : 0.0) : s) * (double)xv[k];
       tile[jl] = s;
     }
     if (accF) *accF += f;
@@ -536,8 +537,8 @@ struct PfKernel {
 #endif
         const Real xa = Ops::propagate(cst, xp[2 * h], z0, y_prop);
         const Real xb = Ops::propagate(cst, xp[2 * h + 1], z1, y_prop);
-        const Real la = Ops::logweight(cst, xa, y_obs);
-        const Real lb = Ops::logweight(cst, xb, y_obs);
+        const Real la = (kFA && y_obs != y_obs) ? (Real)0 : Ops::logweight(cst, xa, y_obs);
+        const Real lb = (kFA && y_obs != y_obs) ? (Real)0 : Ops::logweight(cst, xb, y_obs);
         const int n = nb + 2 * h;
 #ifdef PFB_PROFILE
         if (la == (Real)123456.789) mx = 0.0;
@@ -623,7 +624,9 @@ struct PfKernel {
     const bool resident = n_chunks * kChunk <= p.tile_cap;  // the whole tile stays in shared memory
     const bool last_cta = (j_end == N);
 
-    // ---- generation 0 (standard.py:62-67): stationary draw or fixed value, uniform weights
+    // ---- generation 0 (standard.py:62-67): stationary draw or fixed value, uniform weights (fully
+    //      adapted filter: look-ahead weights p(y_1 | x_0))
+    double mx0 = -INFINITY;
     for (int pp = (j_begin >> 1) + tid; pp < ((j_end + 1) >> 1); pp += BLOCK) {
       Real z[2] = {0, 0};
       if (p.gen_init && !(GENERAL && p.inject)) philox_normal_pair<Real>(p.seed, eval_id, 0u, (uint32_t)pp, z[0], z[1]);
@@ -632,13 +635,16 @@ struct PfKernel {
         const int n = 2 * pp + e;
         if (n >= j_begin && n < j_end) {
           if (p.gen_init && (GENERAL && p.inject)) z[e] = (Real)ld_cg(inj_z0 + n);
-          xr[n] = p.gen_init ? Ops::init(sh_c, z[e]) : (Real)p.initial_state;
-          lwr[n] = (Real)0;
+          const Real x0 = p.gen_init ? Ops::init(sh_c, z[e]) : (Real)p.initial_state;
+          const Real l0 = kFA ? Ops::logweight(sh_c, x0, __ldg(obs + 1)) : (Real)0;
+          xr[n] = x0;
+          lwr[n] = l0;
+          mx0 = dmax(mx0, (double)l0);
           if (p.ws_per_filter) ar[n] = 0;  // generation-0 ancestors are never followed
         }
       }
     }
-    exchange(0.0);
+    exchange(block_max(mx0));
     double m = xchg_max();
     double m_prev = m;  // max log-weight of generation tau-1 (for the deferred smoother job)
 
@@ -669,6 +675,7 @@ struct PfKernel {
         }
         y_obs = __ldg(obs + t);
         y_prop = p.svl_obs_model ? __ldg(obs + t - 1) : y_obs;  // Q10
+        if (kFA) y_obs = (t < T) ? __ldg(obs + t + 1) : CUDART_NAN;  // generation T: uniform weights
       } else {
         u = (GENERAL && p.inject) ? ld_cg(p.inj_u_final + ib) : philox_uniform(p.seed, eval_id, kStreamUFinal, 0u, 0u);
       }
@@ -846,7 +853,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const Device
 // returns (standard.py:96-101, 140-141, 156-169).  One block per filter.
 // ---------------------------------------------------------------------------------------------
 struct FinalizeArgs {
-  int N, T, L, P, B, G, do_smoother;
+  int N, T, L, P, B, G, do_smoother, fully_adapted;
   const double* stat_m; const double* stat_S; const double* filt_part; const double* smo_part;
   double* ll_terms;   // [B][T+1]
   double* log_like;   // [B]
@@ -866,9 +873,14 @@ __global__ void __launch_bounds__(256) pf_finalize_kernel(const FinalizeArgs a) 
   const double S = a.stat_S[bt];
   double f = 0.0;
   for (int g = 0; g < a.G; ++g) f += a.filt_part[bt * a.G + g];
-  const double filt = (t == 0) ? 0.0 : f / S;
+  // bootstrap: weights of generation t carry y_t.  Fully adapted: particles are equally weighted
+  // after the optimal proposal and the weights of generation t-1 carry y_t.
+  const double filt = (t == 0) ? 0.0 : f / (a.fully_adapted ? (double)a.N : S);
   double ll = 0.0;
-  if (t > 0) { ll = a.stat_m[bt]; ll += log(S); ll -= logN; }
+  if (t > 0) {
+    const size_t src = a.fully_adapted ? bt - 1 : bt;
+    ll = a.stat_m[src]; ll += log(a.stat_S[src]); ll -= logN;
+  }
   a.ll_terms[bt] = ll;
   a.filt[bt] = filt;
   if (a.do_smoother) {

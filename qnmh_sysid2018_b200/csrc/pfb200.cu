@@ -87,6 +87,7 @@ KernelFn kernel_for_model(int model) {
 #ifndef PFB_LGSS_ONLY
     case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems, kMinB, GENERAL>;
     case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems, kMinB, GENERAL>;
+    case kModelLGSSFA: return pf_persistent_kernel<kModelLGSSFA, Real, kBlock, kItems, kMinB, GENERAL>;
 #endif
   }
   return nullptr;
@@ -104,11 +105,19 @@ void host_consts(int model, const double* th, double* c) {
   c[C_Q] = std::pow(sv, -2.0);
   c[C_1MPHI] = 1.0 - phi;
   c[C_1MPHI2] = 1.0 - std::pow(phi, 2.0);
-  if (model == kModelLGSS) {
+  if (model == kModelLGSS || model == kModelLGSSFA) {
     const double se = th[3];
     c[C_SIGE_OR_RHO] = se;
     c[C_LOGSIGE] = std::log(se);
     c[C_R] = std::pow(se, -2.0);
+    if (model == kModelLGSSFA) {
+      const double tot = sv * sv + se * se;
+      c[C_STDEV] = std::sqrt(sv * sv * se * se / tot);
+      c[C_FA_A] = se * se / tot;
+      c[C_FA_B] = sv * sv / tot;
+      c[C_SVRHO] = std::sqrt(tot);
+      c[C_RHOTERM] = std::log(std::sqrt(tot));
+    }
   } else if (model == kModelSVL) {
     const double rho = th[3];
     const double rho_term = 1.0 - std::pow(rho, 2.0);
@@ -182,6 +191,7 @@ int pfb200_model_no_params(int model_id) {
     case PFB200_MODEL_LGSS: return 4;
     case PFB200_MODEL_SV: return 3;
     case PFB200_MODEL_SVL: return 4;
+    case PFB200_MODEL_LGSS_FA: return 4;
   }
   return PFB200_EINVAL;
 }
@@ -528,7 +538,7 @@ int pfb200_execute(pfb200_handle* h) {
   }
   CUDA_TRY(cudaEventRecord(h->evk1, h->stream));
   FinalizeArgs fa{};
-  fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G_loc; fa.do_smoother = p.do_smoother;
+  fa.N = p.N; fa.T = p.T; fa.L = p.L; fa.P = p.P; fa.B = p.B; fa.G = p.G_loc; fa.do_smoother = p.do_smoother; fa.fully_adapted = is_fully_adapted(h->model) ? 1 : 0;
   fa.stat_m = p.stat_m; fa.stat_S = p.stat_S; fa.filt_part = p.filt_part; fa.smo_part = p.smo_part;
   fa.ll_terms = h->ll_terms.as<double>(); fa.log_like = h->log_like.as<double>();
   fa.filt = h->filt.as<double>(); fa.smo = h->smo.as<double>(); fa.grad = h->grad.as<double>();

@@ -5,7 +5,8 @@ import numpy as np
 
 from . import _lib as L
 
-MODEL_IDS = {"lgss": L.MODEL_LGSS, "sv": L.MODEL_SV, "sv_leverage": L.MODEL_SVL}
+MODEL_IDS = {"lgss": L.MODEL_LGSS, "sv": L.MODEL_SV, "sv_leverage": L.MODEL_SVL,
+             "lgss_fully_adapted": L.MODEL_LGSS_FA}
 DTYPES = {"float64": L.F64, "fp64": L.F64, "f64": L.F64, "float32": L.F32, "fp32": L.F32, "f32": L.F32}
 RESAMPLING = {"systematic": L.RESAMPLE_SYSTEMATIC, "stratified": L.RESAMPLE_STRATIFIED}
 

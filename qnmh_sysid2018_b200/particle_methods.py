@@ -84,7 +84,10 @@ class ParticleMethodsB200(object):
                          'seed': 87655678,        # helper_linear_gaussian.py:33
                          'store_history': False,  # keep (T+1, N) particles/weights/ancestors
                          'compat': 'numpy',       # Hessian formula: 'numpy' | 'cython'
-                         'svl_obs_index': 'numpy'  # leverage term reads obs[t] | 'model': obs[t-1]
+                         'svl_obs_index': 'numpy',  # leverage term reads obs[t] | 'model': obs[t-1]
+                         # 'bootstrap' (the reference's filter) | 'fully_adapted' (optimal proposal,
+                         # LGSS only; not in the reference -- north star / SURVEY Q13)
+                         'filter_type': 'bootstrap'
                          }
         if new_settings:
             self.settings.update(new_settings)
@@ -112,6 +115,12 @@ class ParticleMethodsB200(object):
     def _evaluate(self, model, do_smoother):
         s = self.settings
         kind = model_kind_of(model)
+        if s['filter_type'] == 'fully_adapted':
+            if kind != 'lgss':
+                raise ValueError("the fully adapted particle filter is only available for the linear Gaussian model")
+            kind = 'lgss_fully_adapted'
+        elif s['filter_type'] != 'bootstrap':
+            raise ValueError("filter_type must be 'bootstrap' or 'fully_adapted'")
         if s['resampling_method'] == 'multinomial':
             raise NotImplementedError("multinomial resampling (resampling.pyx:33-42) has no device path yet: its "
                                       "ancestors are not monotone, which the push-style resampling kernel "

@@ -219,6 +219,35 @@ def test_philox_path_replayed_through_oracle():
     np.testing.assert_allclose(out["grad_terms"][0], ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
 
 
+@pytest.mark.parametrize("N,G", [(3000, 1), (20000, 5)])
+def test_fully_adapted_filter_matches_oracle_and_kalman(N, G):
+    """The fully adapted (optimal proposal) LGSS filter -- not in the reference (Q13) -- against its
+    NumPy restatement on injected randomness (ancestors / particles bit exact) and against the
+    exact Kalman log-likelihood (its estimator has far lower variance than the bootstrap filter)."""
+    from oracle import kalman_oracle as ko
+    rng = np.random.default_rng(N)
+    theta = np.array([0.2, 0.5, 1.0, 0.5])
+    T, L = 40, 5
+    obs = _synthetic_obs("lgss", theta, T, rng)
+    draws = orc.random_draws(rng, N, T)
+    eng = _engine("lgss_fully_adapted", ctas_per_filter=G)
+    out = eng.run(obs, theta, N, L, True, True, 0.0, "systematic", draws=draws, store_history=True)
+    hist = eng.fetch_history()
+    ref = orc.fully_adapted_filter(theta, obs, N, draws)
+    ref.update(orc.fixed_lag_smoother(orc.MODEL_LGSS, theta, obs, ref, L))
+    np.testing.assert_array_equal(hist["ancestors"][0], ref["ancestors"])
+    np.testing.assert_allclose(hist["particles"][0], ref["particles"], rtol=1e-13, atol=1e-14)
+    assert abs(out["log_like"][0] - ref["log_like"]) <= RTOL * abs(ref["log_like"])
+    np.testing.assert_allclose(out["filt"][0], ref["filt_state_est"].reshape(-1), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(out["smo"][0], ref["smo_state_est"].reshape(-1), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(out["grad_terms"][0], ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
+    m0, p0 = ko.stationary_prior(theta)
+    kf = ko.kalman_filter(obs, theta, initial_state=m0, initial_cov=p0)
+    big = _engine("lgss_fully_adapted").run(obs, theta, 1 << 16, L, True, True, 0.0, "systematic", seed=5)
+    assert abs(big["log_like"][0] - kf["log_like"]) < 0.05
+    assert np.abs(big["filt"][0][1:] - kf["filt_state_est"][1:]).max() < 0.02
+
+
 def test_device_normals_match_numpy_box_muller():
     """The device's Philox4x32-10 stream and its custom fp64 log / sqrt / sincospi against a NumPy
     restatement: same bits in, normals equal to a few ulp; moments and tails as expected."""
