@@ -18,7 +18,7 @@ constexpr int kNumConsts = 16;
 constexpr int kModelLGSS = 0, kModelSV = 1, kModelSVL = 2;
 // Fully adapted (optimal-proposal) auxiliary particle filter for the LGSS model: resampling weights
 // p(y_{t+1} | x_t), proposal p(x_{t+1} | x_t, y_{t+1}).  Not in the reference; named by the
-// north star; pinned to the Kalman log-likelihood and to oracle/pf_oracle.py:fully_adapted_filter.
+// north star; pinned to the Kalman log-likelihood and to a NumPy restatement in the test tree.
 constexpr int kModelLGSSFA = 3;
 __host__ __device__ constexpr bool is_fully_adapted(int model) { return model == kModelLGSSFA; }
 
