@@ -1,0 +1,11 @@
+// Launch configuration shared by the kernel instantiation units and the host side.
+#pragma once
+#ifndef PFB_BLOCK
+#define PFB_BLOCK 512
+#endif
+#ifndef PFB_ITEMS
+#define PFB_ITEMS 7
+#endif
+#ifndef PFB_MINB
+#define PFB_MINB 1
+#endif

@@ -348,11 +348,11 @@ struct ModelOps<MODEL, float> {
 // ------------------------------------------------------------------------------------------
 // Taylor coefficients 1/13! ... 1/0! in constant memory: DFMA takes them as constant-bank operands
 // (a 64-bit immediate would cost two extra instructions per Horner step).
-__constant__ double kExpCoef[14] = {
+static __constant__ double kExpCoef[14] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.3888888888888889e-03,
     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
-__constant__ double kExpLn2[3] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+static __constant__ double kExpLn2[3] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
 
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double t = x * kExpLn2[0];

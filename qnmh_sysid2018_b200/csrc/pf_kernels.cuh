@@ -848,6 +848,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const Device
 #endif
 }
 
+#ifdef PFB_UTILITY_KERNELS  // non-template kernels: compiled by the host unit (pfb200.cu) only
 // ---------------------------------------------------------------------------------------------
 // Finalisation: combines the per-CTA partial sums in a fixed order into the outputs the reference
 // returns (standard.py:96-101, 140-141, 156-169).  One block per filter.
@@ -948,5 +949,7 @@ __global__ void pf_philox_uniforms_kernel(unsigned long long seed, unsigned long
                    : philox_uniform(seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)i);
   }
 }
+
+#endif  // PFB_UTILITY_KERNELS
 
 }  // namespace pfb200

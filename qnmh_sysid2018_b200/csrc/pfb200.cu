@@ -10,9 +10,17 @@
 #include <vector>
 
 #include "../../include/pfb200.h"
+#include "pf_config.h"
+#define PFB_UTILITY_KERNELS
 #include "pf_kernels.cuh"
 
 using namespace pfb200;
+
+typedef void (*KernelFn)(const pfb200::DeviceProblem);
+KernelFn pfb200_kernel_lgss(int dtype, bool general);
+KernelFn pfb200_kernel_sv(int dtype, bool general);
+KernelFn pfb200_kernel_svl(int dtype, bool general);
+KernelFn pfb200_kernel_lgss_fa(int dtype, bool general);
 
 namespace {
 
@@ -64,30 +72,20 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-#ifndef PFB_BLOCK
-#define PFB_BLOCK 512
-#endif
-#ifndef PFB_ITEMS
-#define PFB_ITEMS 7
-#endif
-#ifndef PFB_MINB
-#define PFB_MINB 1
-#endif
 constexpr int kBlock = PFB_BLOCK;
 constexpr int kItems = PFB_ITEMS;
-constexpr int kMinB = PFB_MINB;
 constexpr int kChunk = kBlock * kItems;
 
-typedef void (*KernelFn)(const DeviceProblem);
 
-template <typename Real, bool GENERAL>
-KernelFn kernel_for_model(int model) {
+// The persistent kernel is instantiated per model in pf_instances_*.cu (separate translation units,
+// compiled in parallel); each exposes its four flavours through this getter.
+KernelFn kernel_for_model(int model, int dtype, bool general) {
   switch (model) {
-    case kModelLGSS: return pf_persistent_kernel<kModelLGSS, Real, kBlock, kItems, kMinB, GENERAL>;
+    case kModelLGSS: return pfb200_kernel_lgss(dtype, general);
 #ifndef PFB_LGSS_ONLY
-    case kModelSV: return pf_persistent_kernel<kModelSV, Real, kBlock, kItems, kMinB, GENERAL>;
-    case kModelSVL: return pf_persistent_kernel<kModelSVL, Real, kBlock, kItems, kMinB, GENERAL>;
-    case kModelLGSSFA: return pf_persistent_kernel<kModelLGSSFA, Real, kBlock, kItems, kMinB, GENERAL>;
+    case kModelSV: return pfb200_kernel_sv(dtype, general);
+    case kModelSVL: return pfb200_kernel_svl(dtype, general);
+    case kModelLGSSFA: return pfb200_kernel_lgss_fa(dtype, general);
 #endif
   }
   return nullptr;
@@ -217,8 +215,8 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   h->model = model_id;
   h->dtype = dtype;
   h->P = P;
-  h->kernel_fast = dtype == PFB200_F64 ? kernel_for_model<double, false>(model_id) : kernel_for_model<float, false>(model_id);
-  h->kernel_general = dtype == PFB200_F64 ? kernel_for_model<double, true>(model_id) : kernel_for_model<float, true>(model_id);
+  h->kernel_fast = kernel_for_model(model_id, dtype, false);
+  h->kernel_general = kernel_for_model(model_id, dtype, true);
   h->kernel = h->kernel_fast;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
