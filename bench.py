@@ -267,6 +267,13 @@ def gpu_arm(args):
         thetas[:, 1] = np.clip(thetas[:, 1], -0.95, 0.95)
         thetas[:, 2:] = np.abs(thetas[:, 2:])
     eval_ids = np.arange(B, dtype=np.uint64) + np.uint64(rank * B)
+    B_total = B
+    if args.workload == "c3" and world > 1:
+        # the 4096 evaluations are one fixed batch sharded over the ranks (strong scaling); the
+        # Philox stream of an evaluation is keyed by its global index
+        from qnmh_sysid2018_b200.batch import shard_range
+        lo, hi = shard_range(B, rank, world)
+        thetas, eval_ids, B = thetas[lo:hi], np.arange(lo, hi, dtype=np.uint64), hi - lo
 
     stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the events share it
     torch.cuda.set_stream(stream)
@@ -352,7 +359,8 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(t[0]), float(t[1])
 
-    units_per_step = (1 if sharded else world) * B * N * T
+    fixed_job = sharded or (args.workload == "c3" and world > 1)
+    units_per_step = B_total * N * T if fixed_job else world * B * N * T
     value = units_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = units_per_step * args.steps / e2e_s
 
@@ -374,9 +382,9 @@ def gpu_arm(args):
             "metric": "particle-timesteps/sec (PF+fixed-lag smoother)", "value": value,
             "unit": "particle-timesteps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak",
+            "scaling": "strong" if fixed_job else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, model, B, N, T),
+            "config": workload_config(args, model, B_total, N, T),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3},
