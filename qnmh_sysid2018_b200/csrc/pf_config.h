@@ -9,3 +9,6 @@
 #ifndef PFB_MINB
 #define PFB_MINB 1
 #endif
+#ifndef PFB_ITEMS_ALT
+#define PFB_ITEMS_ALT 9
+#endif

@@ -17,10 +17,10 @@
 using namespace pfb200;
 
 typedef void (*KernelFn)(const pfb200::DeviceProblem);
-KernelFn pfb200_kernel_lgss(int dtype, bool general);
-KernelFn pfb200_kernel_sv(int dtype, bool general);
-KernelFn pfb200_kernel_svl(int dtype, bool general);
-KernelFn pfb200_kernel_lgss_fa(int dtype, bool general);
+KernelFn pfb200_kernel_lgss(int dtype, bool general, int items);
+KernelFn pfb200_kernel_sv(int dtype, bool general, int items);
+KernelFn pfb200_kernel_svl(int dtype, bool general, int items);
+KernelFn pfb200_kernel_lgss_fa(int dtype, bool general, int items);
 
 namespace {
 
@@ -73,19 +73,20 @@ struct DevBuf {
 };
 
 constexpr int kBlock = PFB_BLOCK;
-constexpr int kItems = PFB_ITEMS;
+constexpr int kItems = PFB_ITEMS;        // default tile granularity
+constexpr int kItemsAlt = PFB_ITEMS_ALT;  // alternative, chosen when it saves a scan sub-chunk
 constexpr int kChunk = kBlock * kItems;
 
 
 // The persistent kernel is instantiated per model in pf_instances_*.cu (separate translation units,
 // compiled in parallel); each exposes its four flavours through this getter.
-KernelFn kernel_for_model(int model, int dtype, bool general) {
+KernelFn kernel_for_model(int model, int dtype, bool general, int items) {
   switch (model) {
-    case kModelLGSS: return pfb200_kernel_lgss(dtype, general);
+    case kModelLGSS: return pfb200_kernel_lgss(dtype, general, items);
 #ifndef PFB_LGSS_ONLY
-    case kModelSV: return pfb200_kernel_sv(dtype, general);
-    case kModelSVL: return pfb200_kernel_svl(dtype, general);
-    case kModelLGSSFA: return pfb200_kernel_lgss_fa(dtype, general);
+    case kModelSV: return pfb200_kernel_sv(dtype, general, items);
+    case kModelSVL: return pfb200_kernel_svl(dtype, general, items);
+    case kModelLGSSFA: return pfb200_kernel_lgss_fa(dtype, general, items);
 #endif
   }
   return nullptr;
@@ -142,13 +143,13 @@ struct pfb200_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false;
   KernelFn kernel = nullptr;          // flavour selected by the configured problem
-  KernelFn kernel_fast = nullptr;     // Philox + systematic resampling
-  KernelFn kernel_general = nullptr;  // + injected randomness, stratified resampling
+  int items = PFB_ITEMS;              // tile granularity of the selected kernel
   // options
   long long opt_ctas_per_filter = 0;
   long long opt_max_groups = 0;
   long long opt_spin_limit = 20000000LL;
-  long long opt_l2_persist = 0;   // pin the ancestor ring in L2 (access policy window)
+  long long opt_l2_persist = 0;
+  long long opt_items = 0;          // 0 = automatic tile granularity, else PFB_ITEMS / PFB_ITEMS_ALT   // pin the ancestor ring in L2 (access policy window)
   size_t l2_persist_max = 0, l2_window_max = 0;
   // distributed single filter (one process per GPU, peer memory over NVLink)
   long long opt_dist_world = 1, opt_dist_rank = 0;
@@ -215,9 +216,7 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   h->model = model_id;
   h->dtype = dtype;
   h->P = P;
-  h->kernel_fast = kernel_for_model(model_id, dtype, false);
-  h->kernel_general = kernel_for_model(model_id, dtype, true);
-  h->kernel = h->kernel_fast;
+  h->kernel = kernel_for_model(model_id, dtype, false, kItems);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -264,6 +263,7 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
   else if (!strcmp(name, "max_groups")) h->opt_max_groups = value;
   else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
   else if (!strcmp(name, "l2_persist")) h->opt_l2_persist = value;
+  else if (!strcmp(name, "items")) h->opt_items = value;
   else if (!strcmp(name, "dist_world")) {
     if (value < 1 || value > 8) return fail(PFB200_EINVAL, "pfb200_set_option: dist_world must be 1..8");
     h->opt_dist_world = value;
@@ -280,7 +280,8 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "n_groups")) *value = h->prob.n_groups;
   else if (!strcmp(name, "per_cta")) *value = h->prob.per_cta;
   else if (!strcmp(name, "block_threads")) *value = kBlock;
-  else if (!strcmp(name, "chunk")) *value = kChunk;
+  else if (!strcmp(name, "chunk")) *value = kBlock * h->items;
+  else if (!strcmp(name, "items")) *value = h->items;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
   else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
   else if (!strcmp(name, "span")) *value = h->prob.span;
@@ -337,7 +338,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const bool history = (flags & PFB200_FLAG_STORE_HISTORY) != 0;
   CUDA_TRY(cudaSetDevice(h->device));
 
-  h->kernel = (inject || resampling != PFB200_RESAMPLE_SYSTEMATIC) ? h->kernel_general : h->kernel_fast;
+  bool general = inject || resampling != PFB200_RESAMPLE_SYSTEMATIC;  // + the distributed filter (below)
 
   // ---- launch geometry
   const size_t real_sz = h->dtype == PFB200_F64 ? 8 : 4;
@@ -347,33 +348,47 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     if (rank < 0 || rank >= R) return fail(PFB200_EINVAL, "pfb200_configure: dist_rank %d out of range for dist_world %d", rank, R);
     if (B != 1 || history)
       return fail(PFB200_EINVAL, "pfb200_configure: a distributed filter takes n_filters = 1 and no STORE_HISTORY");
-    h->kernel = h->kernel_general;  // the peer-memory paths live in the general flavour
+    general = true;  // the peer-memory paths live in the general flavour
   }
   h->dist_connected = false;
-  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-  int G = 1, G_loc = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0;
+  int G = 1, G_loc = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0, n_chunks = 1;
   size_t smem = 0;
-  for (int pass = 0; pass < 3; ++pass) {
-    // shared memory of the current guess -> co-resident CTAs -> group size
-    smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
-    if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
-    capacity = bps * h->num_sms;
-    if (h->opt_ctas_per_filter > 0) G_loc = (int)h->opt_ctas_per_filter;
-    else if (B == 1) G_loc = ((N + R - 1) / R + kBlock - 1) / kBlock;
-    else G_loc = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
-    if (G_loc > capacity) G_loc = capacity;
-    if (G_loc * R > 1024) G_loc = 1024 / R;
-    if (G_loc < 1) G_loc = 1;
-    G = G_loc * R;
-    per = (N + G - 1) / G;
-    if (G > 1) per = (per + 31) & ~31;  // tile boundaries on 32-particle multiples (aligned stores on
-                                        // every rank; same tiling for any split of G over GPUs)
-    if (R == 1) { G = (N + per - 1) / per; G_loc = G; }  // no empty CTAs on a single GPU
-    const int n_chunks = (per + kChunk - 1) / kChunk;
-    const size_t want = (size_t)n_chunks * kChunk;
-    tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : kChunk;
+  // Two tile granularities are compiled (ITEMS = 7 / 9 parents per thread and scan sub-chunk): take
+  // the alternative when it covers a CTA's parent range with fewer sub-chunks (e.g. N = 4096 per CTA
+  // in the batched mode: one sub-chunk of 4608 instead of 3584 + 512).
+  int items = kItems;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int chunk = kBlock * items;
+    h->kernel = kernel_for_model(h->model, h->dtype, general, items);
+    CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+    G = 1; G_loc = 1; per = N; tile_cap = chunk;
+    for (int pass = 0; pass < 3; ++pass) {
+      // shared memory of the current guess -> co-resident CTAs -> group size
+      smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
+      if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
+      capacity = bps * h->num_sms;
+      if (h->opt_ctas_per_filter > 0) G_loc = (int)h->opt_ctas_per_filter;
+      else if (B == 1) G_loc = ((N + R - 1) / R + kBlock - 1) / kBlock;
+      else G_loc = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
+      if (G_loc > capacity) G_loc = capacity;
+      if (G_loc * R > 1024) G_loc = 1024 / R;
+      if (G_loc < 1) G_loc = 1;
+      G = G_loc * R;
+      per = (N + G - 1) / G;
+      if (G > 1) per = (per + 31) & ~31;  // tile boundaries on 32-particle multiples (aligned stores on
+                                          // every rank; same tiling for any split of G over GPUs)
+      if (R == 1) { G = (N + per - 1) / per; G_loc = G; }  // no empty CTAs on a single GPU
+      n_chunks = (per + chunk - 1) / chunk;
+      const size_t want = (size_t)n_chunks * chunk;
+      tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : chunk;
+    }
+    const int alt_chunks = (per + kBlock * kItemsAlt - 1) / (kBlock * kItemsAlt);
+    if (attempt == 0 && h->opt_items == 0 && alt_chunks < n_chunks) items = kItemsAlt;
+    else if (attempt == 0 && h->opt_items == kItemsAlt) items = kItemsAlt;
+    else break;
   }
+  h->items = items;
   smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
