@@ -12,3 +12,6 @@
 #ifndef PFB_ITEMS_ALT
 #define PFB_ITEMS_ALT 9
 #endif
+#ifndef PFB_ITEMS_SMALL
+#define PFB_ITEMS_SMALL 2  // small filters (<= 1024 particles per CTA): no masked work on empty items
+#endif

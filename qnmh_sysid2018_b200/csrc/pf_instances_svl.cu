@@ -1,6 +1,6 @@
 // Instantiations of the persistent kernel for one model (own translation unit: built in parallel).
 // Two tile granularities: ITEMS = 7 (3584 parents per scan sub-chunk) and ITEMS = 9 (4608; keeps a
-// 4096-particle filter of the batched mode in ONE sub-chunk).
+// 4096-particle filter of the batched mode in ONE sub-chunk); ITEMS = 2 for small filters.
 #include "pf_config.h"
 #include "pf_kernels.cuh"
 
@@ -17,5 +17,6 @@ static KernelFn pick(int dtype, bool general) {
 }
 
 KernelFn pfb200_kernel_svl(int dtype, bool general, int items) {
+  if (items == PFB_ITEMS_SMALL) return pick<PFB_ITEMS_SMALL>(dtype, general);
   return items == PFB_ITEMS_ALT ? pick<PFB_ITEMS_ALT>(dtype, general) : pick<PFB_ITEMS>(dtype, general);
 }

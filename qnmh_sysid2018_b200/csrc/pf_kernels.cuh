@@ -69,6 +69,8 @@ struct DeviceProblem {
   void* x_ring;    // [n_ws][RX][NS] Real
   void* logw;      // [n_ws][RW][NS] Real
   int* anc_ring;   // [n_ws][RA][NS]
+  int anc_smem;    // one CTA per filter and N <= 65535: the ancestor ring lives in shared memory as
+  int anc_stride;  //   uint16 [RA][anc_stride] (lineage walks at shared-memory latency, no global traffic)
   double* xval;    // [n_groups][2][G]
   unsigned* xcount;  // [n_groups] arrival counters (padded to 32 words each)
   int* abort_flag;
@@ -104,6 +106,7 @@ struct PfKernel {
   double* sh_x;    // [G] exchange staging
   double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
+  unsigned short* sh_anc;  // [RA][anc_stride] shared-memory ancestor ring (anc_smem mode)
   const int tid, lane, warp, g_loc, q, g;  // g: CTA index inside the (possibly multi-GPU) group
   const bool dist;                         // several GPUs work on this filter
   const int lo;                            // first global particle index held by this rank
@@ -111,13 +114,15 @@ struct PfKernel {
   const double invN;
   unsigned epoch;
   bool aborted;
+  int sx = 0, sw = 0, sa = 0;  // ring slots of the generation being written (t mod RX / RW / RA)
 #ifdef PFB_PROFILE
   long long prof_acc[kProfSlots] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = 0;
 #endif
 
   __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst)
-      : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst), tid(threadIdx.x),
+      : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst),
+        sh_anc(reinterpret_cast<unsigned short*>(smem + prob.tile_cap + (prob.G > 1 ? prob.G : 1))), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g_loc(blockIdx.x % prob.G_loc),
         q(blockIdx.x / prob.G_loc), g(prob.rank * prob.G_loc + blockIdx.x % prob.G_loc),
         dist(GENERAL && prob.R > 1), lo(prob.rank * prob.span), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
@@ -350,9 +355,17 @@ struct PfKernel {
     return ld_sys(peer_base[r] + (size_t)slot * p.NS + (n - r * p.span));
   }
 
+  // slot k generations before `slot` in a ring of depth R (k <= R)
+  static __device__ __forceinline__ int ring_back(int slot, int k, int R) {
+    const int s = slot - k;
+    return s < 0 ? s + R : s;
+  }
+
+  // lineages of generation tau (ancestor-ring slot `slot_a`) walked back `nlev` generations to
+  // smoothing time i (state-ring slot `si`)
   template <int NI>
   __device__ void smooth_chunk(const Real* lw, double m_tau, const Real* xr, const int* ar,
-                               const double* obs, int tau, int i, int c0, int len,
+                               const double* obs, int nlev, int slot_a, int si, int i, int c0, int len,
                                double (&acc)[kMaxParams + 1]) {
     const size_t NS = (size_t)p.NS;
     const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
@@ -365,17 +378,29 @@ struct PfKernel {
       nxt[k] = cur[k];
       l[k] = (jl < len) ? ld_hint(lw + c0 + jl, once) : (Real)(-INFINITY);
     }
-    int slot = tau % p.RA;
-    const int* a = ar + (size_t)slot * NS;
-    for (int lvl = tau; lvl > i; --lvl) {
+    int slot = slot_a;
+    if (p.anc_smem) {
+      for (int lvl = 0; lvl < nlev; ++lvl) {
+        const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
-      for (int k = 0; k < NI; ++k) {
-        nxt[k] = cur[k];
-        cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+        for (int k = 0; k < NI; ++k) {
+          nxt[k] = cur[k];
+          cur[k] = row[cur[k]];
+        }
+        slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
-      if (slot == 0) { slot = p.RA - 1; a = ar + (size_t)slot * NS; } else { --slot; a -= NS; }
+    } else {
+      for (int lvl = 0; lvl < nlev; ++lvl) {
+        const int* a = ar + (size_t)slot * NS;
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+          nxt[k] = cur[k];
+          cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+        }
+        slot = (slot == 0) ? p.RA - 1 : slot - 1;
+      }
     }
-    const int si = i % p.RX, sn = (i + 1) % p.RX;
+    const int sn = (si + 1 == p.RX) ? 0 : si + 1;
     const Real* xi = xr + (size_t)si * NS;
     const Real* xn = xr + (size_t)sn * NS;
     const double y = __ldg(obs + i);
@@ -413,12 +438,14 @@ struct PfKernel {
   __device__ void smooth_job(const Real* lwr, double m_tau, const Real* xr, const int* ar,
                              const double* obs, int tau, int j_begin, int j_end, int c_lo, int c_hi,
                              double (&acc)[kMaxParams + 1]) {
-    const Real* lw = lwr + (size_t)(tau % p.RW) * p.NS;
+    // tau = t - 2 relative to the generation being written
+    const Real* lw = lwr + (size_t)ring_back(sw, 2, p.RW) * p.NS;
+    const int slot_a = ring_back(sa, 2, p.RA), si = ring_back(sx, p.L + 2, p.RX);
     constexpr int SB = (PFB_SMOOTH_BATCH > 0 && PFB_SMOOTH_BATCH < ITEMS) ? PFB_SMOOTH_BATCH : ITEMS;
     const int first = j_begin + c_lo * kChunk;
     const int last = min(j_end, j_begin + c_hi * kChunk);
     for (int c0 = first; c0 < last; c0 += SB * BLOCK)
-      smooth_chunk<SB>(lw, m_tau, xr, ar, obs, tau, tau - p.L, c0, min(SB * BLOCK, last - c0), acc);
+      smooth_chunk<SB>(lw, m_tau, xr, ar, obs, p.L, slot_a, si, tau - p.L, c0, min(SB * BLOCK, last - c0), acc);
   }
 
   __device__ void write_smooth_partials(int b, int i, double (&acc)[kMaxParams + 1]) {
@@ -475,18 +502,41 @@ struct PfKernel {
     return upper_bound_unrolled<16384>(ta, pos, len);                  // up to 32767 (tile_cap <= 28672)
   }
 
-  // count of tile elements <= pos, knowing that it is >= lo (children are monotone): the next 4
-  // elements are probed at once (independent loads); the full descent only when the answer lies
-  // beyond them (four consecutive parents without offspring)
-  __device__ __forceinline__ int next_parent(uint32_t ta, double pos, int lo, int len, int top) const {
-    int cnt = 0;
+  // the same descent for two positions at once (two independent dependency chains in one basic
+  // block): the first child of this quad and the first child of the next quad
+  template <int TOP>
+  __device__ __forceinline__ void upper_bound_pair_unrolled(uint32_t ta, double pa, double pb, int len,
+                                                            int& la, int& lb) const {
+    la = 0;
+    lb = 0;
 #pragma unroll
-    for (int k = 1; k <= 4; ++k) {
-      const double v = lds_f64(ta + 8u * min(lo + k, len));
-      cnt += (lo + k <= len && v <= pos) ? 1 : 0;
+    for (int step = TOP; step > 0; step >>= 1) {
+      const int qa = min(la + step, len), qb = min(lb + step, len);
+      const double va = lds_f64(ta + 8u * qa), vb = lds_f64(ta + 8u * qb);
+      la = (va <= pa) ? qa : la;
+      lb = (vb <= pb) ? qb : lb;
     }
-    if (cnt == 4 && lo + 4 < len) return upper_bound_tile(ta, pos, len, top);
-    return lo + cnt;
+  }
+  __device__ __forceinline__ void upper_bound_pair(uint32_t ta, double pa, double pb, int len, int top,
+                                                   int& la, int& lb) const {
+    if (top <= 512) upper_bound_pair_unrolled<512>(ta, pa, pb, len, la, lb);
+    else if (top <= 4096) upper_bound_pair_unrolled<4096>(ta, pa, pb, len, la, lb);
+    else upper_bound_pair_unrolled<16384>(ta, pa, pb, len, la, lb);
+  }
+
+  // counts for the three inner children of a quad, known to lie in [la, lb] (positions are
+  // monotone in the child index): three independent descents over the window, usually 0-3 levels
+  __device__ __forceinline__ void upper_bound_window3(uint32_t ta, const double (&pos)[3], int la, int lb,
+                                                      int (&l)[3]) const {
+    l[0] = l[1] = l[2] = la;
+    const int span = lb - la;
+    for (int step = (span > 0) ? (1 << (31 - __clz(span))) : 0; step > 0; step >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const int qe = min(l[e] + step, lb);
+        l[e] = (lds_f64(ta + 8u * qe) <= pos[e]) ? qe : l[e];
+      }
+    }
   }
 
   // ---- children of the normalised CDF tile: resample + propagate + weight (phase B).  A thread
@@ -500,22 +550,28 @@ struct PfKernel {
     while (top * 2 <= len) top *= 2;
     const uint32_t ta = smem_base(tile) - 8u;  // address of tile[-1]
     const uint64_t keep = l2_policy_evict_last();
+    unsigned short* anc_sh = sh_anc + (size_t)sa * p.anc_stride;  // generation-t row (anc_smem mode)
     double cst[kNumConsts];
     load_step_consts<MODEL>(smem_base(sh_c), cst);
     for (int qq = q0 + tid; qq < q1; qq += BLOCK) {
       const int nb = 4 * qq;
       const bool full = nb >= n_lo && nb + 3 < n_hi;
       int j[4];
-      int lo = -1;
+      {
+        // first child of this quad and of the next one side by side, then the inner three children
+        // inside the window the two answers span (never a second full descent)
+        const double pa = position(nb, u, t, inj_u_t, eval_id);
+        const double pb = (nb + 4 < p.N) ? position(nb + 4, u, t, inj_u_t, eval_id) : INFINITY;
+        double pin[3];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = nb + e;
-        j[e] = 0;
-        if (full || (n >= n_lo && n < n_hi)) {
-          const double pos = position(n, u, t, inj_u_t, eval_id);
-          lo = (lo < 0) ? upper_bound_tile(ta, pos, len, top) : next_parent(ta, pos, lo, len, top);
-          j[e] = min(lo, len - 1);
-        }
+        for (int e = 0; e < 3; ++e)
+          pin[e] = (nb + 1 + e < p.N) ? position(nb + 1 + e, u, t, inj_u_t, eval_id) : INFINITY;
+        int la, lb, li[3];
+        upper_bound_pair(ta, pa, pb, len, top, la, lb);
+        upper_bound_window3(ta, pin, la, lb, li);
+        j[0] = min(la, len - 1);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) j[1 + e] = min(li[e], len - 1);
       }
       PFB_TICK(11);
       Real xp[4];
@@ -548,11 +604,12 @@ struct PfKernel {
           mx = dmax(mx, dmax((double)la, (double)lb));
           store2(x_new + n, xa, xb);
           store2(lw_new + n, la, lb);
-          if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(c0 + j[2 * h], c0 + j[2 * h + 1]);
+          if (p.anc_smem) *reinterpret_cast<ushort2*>(anc_sh + n) = make_ushort2((unsigned short)(c0 + j[2 * h]), (unsigned short)(c0 + j[2 * h + 1]));
+          else if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(c0 + j[2 * h], c0 + j[2 * h + 1]);
           else st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
         } else {
-          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
-          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
+          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
         }
         PFB_TICK(15);
       }
@@ -578,9 +635,9 @@ struct PfKernel {
         children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
                        y_obs, c0, len, s_lo, s_hi, false, mx);
       } else {  // global-index views of rank r's generation-t rows
-        Real* xv = reinterpret_cast<Real*>(p.peer_x[r]) + (size_t)(t % p.RX) * NS - (size_t)r * p.span;
-        Real* lv = reinterpret_cast<Real*>(p.peer_lw[r]) + (size_t)(t % p.RW) * NS - (size_t)r * p.span;
-        int* av = p.peer_anc[r] + (size_t)(t % p.RA) * NS - (size_t)r * p.span;
+        Real* xv = reinterpret_cast<Real*>(p.peer_x[r]) + (size_t)sx * NS - (size_t)r * p.span;
+        Real* lv = reinterpret_cast<Real*>(p.peer_lw[r]) + (size_t)sw * NS - (size_t)r * p.span;
+        int* av = p.peer_anc[r] + (size_t)sa * NS - (size_t)r * p.span;
         children_chunk(tile, x_prev, xv, lv, av, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs, c0,
                        len, s_lo, s_hi, true, mx);
       }
@@ -645,14 +702,18 @@ struct PfKernel {
       }
     }
     exchange(block_max(mx0));
+    sx = sw = sa = 0;  // generation 0 lives in slot 0 of every ring
     double m = xchg_max();
     double m_prev = m;  // max log-weight of generation tau-1 (for the deferred smoother job)
 
     for (int t = 1; t <= T + 1; ++t) {
       if (aborted) return;
       const int tau = t - 1;
-      const Real* x_prev = xr + (size_t)(tau % p.RX) * NS;
-      const Real* lw_prev = lwr + (size_t)(tau % p.RW) * NS;
+      const Real* x_prev = xr + (size_t)sx * NS;  // generation tau: the slots written last step
+      const Real* lw_prev = lwr + (size_t)sw * NS;
+      sx = (sx + 1 == p.RX) ? 0 : sx + 1;
+      sw = (sw + 1 == p.RW) ? 0 : sw + 1;
+      sa = (sa + 1 == p.RA) ? 0 : sa + 1;
       const bool final_step = (t == T + 1);
       // Deferred smoother job of this step: lag time tau-1 (its weights, ancestors and states are
       // final), split over the two exchange waits.  Lag time T is handled by the tail below.
@@ -732,16 +793,16 @@ struct PfKernel {
           double ta[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
           for (int c = 0; c < n_chunks; ++c) {
             const int c0 = j_begin + c * kChunk;
-            smooth_chunk<ITEMS>(lw_prev, m, xr, ar, obs, tau, i, c0, min(kChunk, j_end - c0), ta);
+            smooth_chunk<ITEMS>(lw_prev, m, xr, ar, obs, tau - i, ring_back(sa, 1, p.RA), ring_back(sx, T + 1 - i, p.RX), i, c0, min(kChunk, j_end - c0), ta);
           }
           write_smooth_partials(b, i, ta);
         }
       }
 
       // ---------------- phase B
-      Real* x_new = xr + (size_t)(t % p.RX) * NS;
-      Real* lw_new = lwr + (size_t)(t % p.RW) * NS;
-      int* anc_new = ar + (size_t)(t % p.RA) * NS;
+      Real* x_new = xr + (size_t)sx * NS;
+      Real* lw_new = lwr + (size_t)sw * NS;
+      int* anc_new = ar + (size_t)sa * NS;
       PFB_TICK(3);
       double mx = -INFINITY;
       int traj_cnt = 0;
@@ -810,7 +871,8 @@ struct PfKernel {
           int k = ld_cg(p.traj_k + b);
           if (k > N - 1) k = N - 1;
           // distributed: the count is a per-rank partial and the row may live elsewhere (not drawn)
-          p.traj_idx[b] = dist ? -1 : ld_cg(ar + (size_t)(T % p.RA) * NS + k);
+          p.traj_idx[b] = dist ? -1 : (p.anc_smem ? (int)sh_anc[(size_t)ring_back(sa, 1, p.RA) * p.anc_stride + k]
+                                                    : ld_cg(ar + (size_t)ring_back(sa, 1, p.RA) * NS + k));
         }
       } else {
         PFB_TICK(4);

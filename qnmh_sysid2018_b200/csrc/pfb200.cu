@@ -75,6 +75,7 @@ struct DevBuf {
 constexpr int kBlock = PFB_BLOCK;
 constexpr int kItems = PFB_ITEMS;        // default tile granularity
 constexpr int kItemsAlt = PFB_ITEMS_ALT;  // alternative, chosen when it saves a scan sub-chunk
+constexpr int kItemsSmall = PFB_ITEMS_SMALL;  // small filters: a CTA's parent range fits 2 per thread
 constexpr int kChunk = kBlock * kItems;
 
 
@@ -149,6 +150,7 @@ struct pfb200_handle {
   long long opt_max_groups = 0;
   long long opt_spin_limit = 20000000LL;
   long long opt_l2_persist = 0;
+  long long opt_anc_smem = 1;       // shared-memory ancestor ring for one-CTA filters
   long long opt_items = 0;          // 0 = automatic tile granularity, else PFB_ITEMS / PFB_ITEMS_ALT   // pin the ancestor ring in L2 (access policy window)
   size_t l2_persist_max = 0, l2_window_max = 0;
   // distributed single filter (one process per GPU, peer memory over NVLink)
@@ -264,6 +266,7 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
   else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
   else if (!strcmp(name, "l2_persist")) h->opt_l2_persist = value;
   else if (!strcmp(name, "items")) h->opt_items = value;
+  else if (!strcmp(name, "anc_smem")) h->opt_anc_smem = value;
   else if (!strcmp(name, "dist_world")) {
     if (value < 1 || value > 8) return fail(PFB200_EINVAL, "pfb200_set_option: dist_world must be 1..8");
     h->opt_dist_world = value;
@@ -282,6 +285,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "block_threads")) *value = kBlock;
   else if (!strcmp(name, "chunk")) *value = kBlock * h->items;
   else if (!strcmp(name, "items")) *value = h->items;
+  else if (!strcmp(name, "anc_smem")) *value = h->prob.anc_smem;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
   else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
   else if (!strcmp(name, "span")) *value = h->prob.span;
@@ -384,12 +388,19 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
       tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : chunk;
     }
     const int alt_chunks = (per + kBlock * kItemsAlt - 1) / (kBlock * kItemsAlt);
-    if (attempt == 0 && h->opt_items == 0 && alt_chunks < n_chunks) items = kItemsAlt;
+    if (attempt == 0 && (h->opt_items == kItemsSmall || (h->opt_items == 0 && per <= kBlock * kItemsSmall))) items = kItemsSmall;
+    else if (attempt == 0 && h->opt_items == 0 && alt_chunks < n_chunks) items = kItemsAlt;
     else if (attempt == 0 && h->opt_items == kItemsAlt) items = kItemsAlt;
     else break;
   }
   h->items = items;
-  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
+  // Shared-memory ancestor ring: one CTA per filter, indices fit 16 bits, ring + CDF tile fit.
+  const int RA_ring = L + 2;
+  const int anc_stride = (N + 7) & ~7;
+  const size_t anc_bytes = (size_t)RA_ring * anc_stride * sizeof(unsigned short);
+  const bool anc_smem = h->opt_anc_smem && G == 1 && R == 1 && !history && do_smoother && N <= 65535 &&
+                        (size_t)(tile_cap + 1) * sizeof(double) + anc_bytes <= smem_limit;
+  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes : 0);
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
   capacity = bps * h->num_sms;
@@ -425,6 +436,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.inject_per_filter = (flags & PFB200_FLAG_INJECT_PER_FILTER) ? 1 : 0;
   p.obs_per_filter = (flags & PFB200_FLAG_OBS_PER_FILTER) ? 1 : 0;
   p.ws_per_filter = history ? 1 : 0;
+  p.anc_smem = anc_smem ? 1 : 0;
+  p.anc_stride = anc_stride;
   p.initial_state = initial_state;
   p.seed = seed;
   p.spin_limit = h->opt_spin_limit;
