@@ -59,6 +59,7 @@ struct DeviceProblem {
   double initial_state;
   unsigned long long seed;
   long long spin_limit;
+  unsigned long long pol_keep, pol_once;  // L2 cache policies (evict_last / evict_first), created once per handle
   const double* obs;
   const double* consts;              // [B][kNumConsts]
   const unsigned long long* eval_ids;  // [B]
@@ -350,9 +351,17 @@ struct PfKernel {
   template <typename T>
   __device__ __forceinline__ T ld_ring(const T* local_row_view, T* const* peer_base, int slot, int n,
                                        uint64_t pol) const {
-    if (!dist || (unsigned)(n - lo) < (unsigned)p.span) return ld_hint(local_row_view + n, pol);
+    if (!dist || (unsigned)(n - lo) < (unsigned)p.span) return ld_hint(local_row_view + (unsigned)n, pol);  // n >= 0: one IMAD.WIDE.U32
     const int r = n / p.span;
     return ld_sys(peer_base[r] + (size_t)slot * p.NS + (n - r * p.span));
+  }
+
+  // Hides how a row pointer was derived, so that row[index] compiles to ONE IMAD.WIDE.U32 on a
+  // register pair instead of re-deriving base + (row offset + index) * size per access.
+  template <typename T>
+  static __device__ __forceinline__ const T* opaque(const T* ptr) {
+    asm volatile("" : "+l"(ptr));
+    return ptr;
   }
 
   // slot k generations before `slot` in a ring of depth R (k <= R)
@@ -368,7 +377,7 @@ struct PfKernel {
                                const double* obs, int nlev, int slot_a, int si, int i, int c0, int len,
                                double (&acc)[kMaxParams + 1]) {
     const size_t NS = (size_t)p.NS;
-    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+    const uint64_t keep = p.pol_keep, once = p.pol_once;
     int cur[NI], nxt[NI];
     Real l[NI];
 #pragma unroll
@@ -378,31 +387,42 @@ struct PfKernel {
       nxt[k] = cur[k];
       l[k] = (jl < len) ? ld_hint(lw + c0 + jl, once) : (Real)(-INFINITY);
     }
+    // nlev - 1 hops to the ancestors at time i+1, then one more to time i
     int slot = slot_a;
     if (p.anc_smem) {
-      for (int lvl = 0; lvl < nlev; ++lvl) {
+      for (int lvl = 1; lvl < nlev; ++lvl) {
+        const unsigned short* row = sh_anc + slot * p.anc_stride;
+#pragma unroll
+        for (int k = 0; k < NI; ++k) cur[k] = row[cur[k]];
+        slot = (slot == 0) ? p.RA - 1 : slot - 1;
+      }
+      if (nlev > 0) {
         const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
           nxt[k] = cur[k];
           cur[k] = row[cur[k]];
         }
-        slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
     } else {
-      for (int lvl = 0; lvl < nlev; ++lvl) {
-        const int* a = ar + (size_t)slot * NS;
+      for (int lvl = 1; lvl < nlev; ++lvl) {
+        const int* a = opaque(ar + (size_t)slot * NS);
+#pragma unroll
+        for (int k = 0; k < NI; ++k) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+        slot = (slot == 0) ? p.RA - 1 : slot - 1;
+      }
+      if (nlev > 0) {
+        const int* a = opaque(ar + (size_t)slot * NS);
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
           nxt[k] = cur[k];
           cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
         }
-        slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
     }
     const int sn = (si + 1 == p.RX) ? 0 : si + 1;
-    const Real* xi = xr + (size_t)si * NS;
-    const Real* xn = xr + (size_t)sn * NS;
+    const Real* xi = opaque(xr + (size_t)si * NS);
+    const Real* xn = opaque(xr + (size_t)sn * NS);
     const double y = __ldg(obs + i);
     Real xc[NI], xnext[NI];
 #pragma unroll
@@ -549,10 +569,11 @@ struct PfKernel {
     int top = 1;
     while (top * 2 <= len) top *= 2;
     const uint32_t ta = smem_base(tile) - 8u;  // address of tile[-1]
-    const uint64_t keep = l2_policy_evict_last();
+    const uint64_t keep = p.pol_keep;
     unsigned short* anc_sh = sh_anc + (size_t)sa * p.anc_stride;  // generation-t row (anc_smem mode)
     double cst[kNumConsts];
     load_step_consts<MODEL>(smem_base(sh_c), cst);
+    const Real* xp_row = opaque(x_prev + c0);
     for (int qq = q0 + tid; qq < q1; qq += BLOCK) {
       const int nb = 4 * qq;
       const bool full = nb >= n_lo && nb + 3 < n_hi;
@@ -576,7 +597,7 @@ struct PfKernel {
       PFB_TICK(11);
       Real xp[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) xp[e] = ld_cg(x_prev + c0 + j[e]);
+      for (int e = 0; e < 4; ++e) xp[e] = ld_cg(xp_row + (unsigned)j[e]);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
         Real z0, z1;
@@ -1010,6 +1031,12 @@ __global__ void pf_philox_uniforms_kernel(unsigned long long seed, unsigned long
     u[i] = (t < 0) ? philox_uniform(seed, eval_id, kStreamUFinal, 0u, 0u)
                    : philox_uniform(seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)i);
   }
+}
+
+// the two L2 cache-policy descriptors the persistent kernel takes as parameters
+__global__ void pf_policy_kernel(unsigned long long* out) {
+  out[0] = l2_policy_evict_last();
+  out[1] = l2_policy_evict_first();
 }
 
 #endif  // PFB_UTILITY_KERNELS

@@ -138,6 +138,7 @@ struct pfb200_handle {
   int dtype = 0;
   int P = 0;
   int num_sms = 0;
+  unsigned long long pol_keep = 0, pol_once = 0;  // L2 cache-policy descriptors (device-created)
   int blocks_per_sm = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
@@ -230,6 +231,17 @@ int pfb200_create(int device, int model_id, int dtype, pfb200_handle** out) {
   CUDA_TRY(cudaEventCreate(&h->ev1));
   CUDA_TRY(cudaEventCreate(&h->evk0));
   CUDA_TRY(cudaEventCreate(&h->evk1));
+  {
+    unsigned long long* dpol = nullptr;
+    unsigned long long hpol[2] = {0, 0};
+    CUDA_TRY(cudaMalloc(&dpol, sizeof(hpol)));
+    pf_policy_kernel<<<1, 1, 0, h->stream>>>(dpol);
+    CUDA_TRY(cudaMemcpyAsync(hpol, dpol, sizeof(hpol), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaFree(dpol));
+    h->pol_keep = hpol[0];
+    h->pol_once = hpol[1];
+  }
   *out = h;
   return PFB200_OK;
 }
@@ -441,6 +453,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.initial_state = initial_state;
   p.seed = seed;
   p.spin_limit = h->opt_spin_limit;
+  p.pol_keep = h->pol_keep;
+  p.pol_once = h->pol_once;
   h->flags = flags;
 
   // ---- buffers
