@@ -19,8 +19,8 @@
  *     python/state/particle_methods/cython_sv_leverage_helper.pyx:35,146
  *   ParticleMethods.filter / .smoother (NumPy twin, run-time N/T/L)    same calls; semantics follow
  *     python/state/particle_methods/standard.py:42,121                 the NumPy path
- *   systematic / stratified resampling                                 `resampling` argument
- *     python/state/particle_methods/resampling.pyx:44,65
+ *   systematic / stratified / multinomial resampling                   `resampling` argument
+ *     python/state/particle_methods/resampling.pyx:33,44,65
  *
  * Conventions: every pointer is a HOST pointer owned by the caller unless stated otherwise; arrays
  * are C-contiguous doubles in time-major order; the library owns all device memory inside the
@@ -57,6 +57,7 @@ extern "C" {
 /* resampling (resampling.pyx) */
 #define PFB200_RESAMPLE_SYSTEMATIC 0
 #define PFB200_RESAMPLE_STRATIFIED 1
+#define PFB200_RESAMPLE_MULTINOMIAL 2 /* resampling.pyx:33-42; per-particle uniforms like stratified; not for distributed filters */
 
 /* flags (bit mask) */
 #define PFB200_FLAG_STORE_HISTORY 1u    /* keep all T+1 generations (particles, log-weights, ancestors) */

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(HERE, "csrc", "libpfb200
 
 MODEL_LGSS, MODEL_SV, MODEL_SVL, MODEL_LGSS_FA = 0, 1, 2, 3
 F64, F32 = 0, 1
-RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED = 0, 1
+RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 FLAG_STORE_HISTORY, FLAG_OBS_PER_FILTER, FLAG_SVL_OBS_MODEL, FLAG_INJECT_PER_FILTER = 1, 2, 4, 8
 ABI_VERSION = 1
 

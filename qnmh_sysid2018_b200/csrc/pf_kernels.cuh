@@ -80,6 +80,7 @@ struct DeviceProblem {
   double* filt_part;  // [B][T+1][G]
   double* smo_part;   // [B][T+1][G][P+1]
   int* traj_k;        // [B]
+  double* cdf_g;      // [n_ws][NS] normalised CDF in global memory (multinomial resampling only)
   int* traj_idx;      // [B]
   long long* prof;    // [grid][kProfSlots] per-phase cycle counters (PFB_PROFILE builds only)
   // peer-memory views of every rank's rings / exchange buffers (entry `rank` = own memory)
@@ -578,7 +579,25 @@ struct PfKernel {
       const int nb = 4 * qq;
       const bool full = nb >= n_lo && nb + 3 < n_hi;
       int j[4];
-      {
+      if (GENERAL && p.resampling == 2) {
+        // multinomial: j = #{ k < N-1 : cdf[k] < u_n } (searchsorted side='left' with the last CDF
+        // entry forced to 1 > u_n), four descents over the global CDF side by side
+        const int top_g = 1 << (31 - __clz(max(p.N - 1, 1)));
+        double un[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = min(nb + e, p.N - 1);
+          un[e] = p.inject ? ld_cg(inj_u_t + n) : philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, (uint32_t)n);
+          j[e] = 0;
+        }
+        for (int step = top_g; step > 0; step >>= 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int probe = min(j[e] + step, p.N - 1);
+            if (probe > 0 && ld_cg(tile + probe - 1) < un[e]) j[e] = probe;
+          }
+        }
+      } else {
         // first child of this quad and of the next one side by side, then the inner three children
         // inside the window the two answers span (never a second full descent)
         const double pa = position(nb, u, t, inj_u_t, eval_id);
@@ -687,7 +706,7 @@ struct PfKernel {
     const unsigned long long eval_id = p.eval_ids[b];
     const size_t ib = p.inject_per_filter ? (size_t)b : 0;
     const double* inj_z0 = (GENERAL && p.inject) ? p.inj_z0 + ib * N : nullptr;
-    const size_t u_row = ((GENERAL && p.resampling == 1)) ? (size_t)N : 1;
+    const size_t u_row = ((GENERAL && p.resampling != 0)) ? (size_t)N : 1;
     const double* inj_u = (GENERAL && p.inject) ? p.inj_u + ib * (T + 1) * u_row : nullptr;
     const double* inj_z = (GENERAL && p.inject) ? p.inj_z + ib * (size_t)(T + 1) * N : nullptr;
 
@@ -751,7 +770,7 @@ struct PfKernel {
         if ((GENERAL && p.inject)) {
           inj_u_t = inj_u + (size_t)t * u_row;
           inj_z_t = inj_z + (size_t)t * N;
-          u = ((GENERAL && p.resampling == 1)) ? 0.0 : ld_cg(inj_u_t);
+          u = ((GENERAL && p.resampling != 0)) ? 0.0 : ld_cg(inj_u_t);
         } else if ((!GENERAL || p.resampling == 0)) {
           u = philox_uniform(p.seed, eval_id, kStreamU, (uint32_t)t, 0u);
         }
@@ -794,7 +813,8 @@ struct PfKernel {
       xchg_prefix(Pg, Pg1, S);
       const double invS = 1.0 / S;  // the CDF is (prefix sum) * (1/S) everywhere
       int n_begin = 0, n_end = 0;
-      if (!final_step) {
+      const bool pull = GENERAL && p.resampling == 2;  // multinomial: children pull from the global CDF
+      if (!final_step && !pull) {
         int nb = 0;
         if (lane == 0) nb = (g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg, invS), u, t, inj_u_t, eval_id);
         if (lane == 1) nb = last_cta ? N : lower_bound_child(__dmul_rn(Pg1, invS), u, t, inj_u_t, eval_id);
@@ -845,6 +865,9 @@ struct PfKernel {
           // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
           for (int jl = tid; jl < own; jl += BLOCK)
             if (sh_s[jl] <= u) ++traj_cnt;
+        } else if (pull) {
+          double* cg = p.cdf_g + (size_t)ws * NS - lo;
+          for (int jl = tid; jl < own; jl += BLOCK) cg[j_begin + jl] = sh_s[jl];
         } else {
           children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
                        y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
@@ -870,6 +893,13 @@ struct PfKernel {
               const int jl = k * BLOCK + tid;
               if (jl < len && sh_s[jl] <= u) ++traj_cnt;
             }
+          } else if (pull) {
+            double* cg = p.cdf_g + (size_t)ws * NS - lo;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+              const int jl = k * BLOCK + tid;
+              if (jl < len) cg[c0 + jl] = sh_s[jl];
+            }
           } else {
             const double next_base = base + chunk_total;
             int n_hi = n_end;
@@ -883,6 +913,13 @@ struct PfKernel {
           }
           base += chunk_total;
         }
+      }
+      if (pull && !final_step) {
+        // every CTA's part of the CDF is published; the children of this CTA's own index range
+        // search all of it (resampling.pyx:33-42: unsorted uniforms, ancestors in any tile)
+        exchange(0.0);
+        children_chunk(p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
+                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, mx);
       }
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);

@@ -169,7 +169,7 @@ struct pfb200_handle {
   int n_ws = 0;
   // device buffers
   DevBuf obs, consts, evals, inj_z0, inj_u, inj_z, inj_uf;
-  DevBuf x_ring, logw, anc, xval, xcount, abortf;
+  DevBuf x_ring, logw, anc, cdf_g, xval, xcount, abortf;
   DevBuf stat_m, stat_S, filt_part, smo_part, traj_k, traj_idx;
   DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch, prof;
   std::vector<double> h_consts;
@@ -344,7 +344,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   if (N > (1 << 30)) return fail(PFB200_EINVAL, "pfb200_configure: no_particles %d exceeds 2^30", N);
   if (do_smoother && L < 1)
     return fail(PFB200_EINVAL, "pfb200_configure: the fixed-lag smoother needs fixed_lag >= 1 (the reference raises NameError at standard.py:161 for fixed_lag=0)");
-  if (resampling != PFB200_RESAMPLE_SYSTEMATIC && resampling != PFB200_RESAMPLE_STRATIFIED)
+  if (resampling != PFB200_RESAMPLE_SYSTEMATIC && resampling != PFB200_RESAMPLE_STRATIFIED &&
+      resampling != PFB200_RESAMPLE_MULTINOMIAL)
     return fail(PFB200_EINVAL, "pfb200_configure: unsupported resampling method %d", resampling);
   if (!obs || !theta) return fail(PFB200_EINVAL, "pfb200_configure: obs and theta are required");
   const int n_inj = (inj_z0 != nullptr) + (inj_u != nullptr) + (inj_z != nullptr) + (inj_u_final != nullptr);
@@ -362,6 +363,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const int R = (int)h->opt_dist_world, rank = (int)h->opt_dist_rank;
   if (R > 1) {
     if (rank < 0 || rank >= R) return fail(PFB200_EINVAL, "pfb200_configure: dist_rank %d out of range for dist_world %d", rank, R);
+    if (resampling == PFB200_RESAMPLE_MULTINOMIAL)
+      return fail(PFB200_EINVAL, "pfb200_configure: multinomial resampling is not available for a distributed filter");
     if (B != 1 || history)
       return fail(PFB200_EINVAL, "pfb200_configure: a distributed filter takes n_filters = 1 and no STORE_HISTORY");
     general = true;  // the peer-memory paths live in the general flavour
@@ -461,7 +464,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const size_t T1 = (size_t)T + 1;
   const size_t n_obs_rows = p.obs_per_filter ? B : 1;
   const size_t n_injr = p.inject_per_filter ? B : 1;
-  const size_t u_row = resampling == PFB200_RESAMPLE_STRATIFIED ? (size_t)N : 1;
+  const size_t u_row = resampling != PFB200_RESAMPLE_SYSTEMATIC ? (size_t)N : 1;
   CUDA_TRY(h->obs.reserve(n_obs_rows * T1 * 8));
   CUDA_TRY(h->consts.reserve((size_t)B * kNumConsts * 8));
   CUDA_TRY(h->evals.reserve((size_t)B * 8));
@@ -474,6 +477,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * p.NS * real_sz));
   CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
   CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
+  if (resampling == PFB200_RESAMPLE_MULTINOMIAL) CUDA_TRY(h->cdf_g.reserve((size_t)h->n_ws * p.NS * 8));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
   CUDA_TRY(h->xcount.reserve((size_t)n_groups * 32 * 4));
   CUDA_TRY(h->abortf.reserve(16));
@@ -509,6 +513,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.filt_part = h->filt_part.as<double>();
   p.smo_part = h->smo_part.as<double>();
   p.traj_k = h->traj_k.as<int>();
+  p.cdf_g = h->cdf_g.as<double>();
   p.traj_idx = h->traj_idx.as<int>();
   p.prof = h->prof.as<long long>();
   for (int r = 0; r < 8; ++r) { p.peer_x[r] = p.x_ring; p.peer_lw[r] = p.logw; p.peer_anc[r] = p.anc_ring; p.peer_xval[r] = p.xval; p.peer_xcount[r] = p.xcount; }

@@ -8,7 +8,8 @@ from . import _lib as L
 MODEL_IDS = {"lgss": L.MODEL_LGSS, "sv": L.MODEL_SV, "sv_leverage": L.MODEL_SVL,
              "lgss_fully_adapted": L.MODEL_LGSS_FA}
 DTYPES = {"float64": L.F64, "fp64": L.F64, "f64": L.F64, "float32": L.F32, "fp32": L.F32, "f32": L.F32}
-RESAMPLING = {"systematic": L.RESAMPLE_SYSTEMATIC, "stratified": L.RESAMPLE_STRATIFIED}
+RESAMPLING = {"systematic": L.RESAMPLE_SYSTEMATIC, "stratified": L.RESAMPLE_STRATIFIED,
+              "multinomial": L.RESAMPLE_MULTINOMIAL}
 
 
 def _dptr(a):
@@ -89,7 +90,7 @@ class Engine(object):
             flags |= L.FLAG_SVL_OBS_MODEL
         z0 = u = z = uf = None
         if draws is not None:
-            strat = resampling == "stratified"
+            strat = resampling in ("stratified", "multinomial")  # one uniform per particle
             ushape = (T + 1, N) if strat else (T + 1,)
             if isinstance(draws, (list, tuple)):
                 if len(draws) != B:

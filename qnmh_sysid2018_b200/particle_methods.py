@@ -121,11 +121,7 @@ class ParticleMethodsB200(object):
             kind = 'lgss_fully_adapted'
         elif s['filter_type'] != 'bootstrap':
             raise ValueError("filter_type must be 'bootstrap' or 'fully_adapted'")
-        if s['resampling_method'] == 'multinomial':
-            raise NotImplementedError("multinomial resampling (resampling.pyx:33-42) has no device path yet: its "
-                                      "ancestors are not monotone, which the push-style resampling kernel "
-                                      "relies on; use 'systematic' (all reference scripts) or 'stratified'")
-        if s['resampling_method'] not in ('systematic', 'stratified'):
+        if s['resampling_method'] not in ('systematic', 'stratified', 'multinomial'):
             raise ValueError("Unknown resampling method selected...")
         engine = self._get_engine(kind)
         obs = np.asarray(model.obs, dtype=np.float64).reshape(-1)

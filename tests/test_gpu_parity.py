@@ -62,8 +62,6 @@ def _compare(eng, kind, theta, obs, N, L, draws, resampling="systematic", gen_in
 def test_cuda_matches_reference_golden(name):
     """The CUDA path replays the reference's own random stream and must reproduce its outputs."""
     g = gu.load(name)
-    if g["resampling_method"] == "multinomial":
-        pytest.skip("multinomial resampling is a next-tier row (SURVEY 8 a3')")
     eng = _engine(g["model_kind"])
     draws = gu.draws_for(g)
     out = eng.run(g["obs"], g["theta"], g["no_particles"], g["fixed_lag"], True,
@@ -151,6 +149,38 @@ def test_stratified_resampling_matches_oracle():
     for N, G in ((500, 1), (8000, 3)):
         draws = orc.random_draws(rng, N, 30, resampling="stratified")
         _compare(_engine("lgss", ctas_per_filter=G), "lgss", theta, obs, N, 5, draws, resampling="stratified")
+
+
+def test_multinomial_resampling_matches_oracle():
+    """resampling.pyx:33-42: unsorted per-particle uniforms, ancestors in any CTA's tile (pull-style
+    search of the global CDF): one CTA, several CTAs, streaming tiles, ring and history storage."""
+    rng = np.random.default_rng(12)
+    theta = np.array([0.2, 0.5, 1.0, 0.5])
+    obs = _synthetic_obs("lgss", theta, 25, rng)
+    for N, G in ((1, 1), (500, 1), (8000, 3), (70001, 2)):
+        draws = orc.random_draws(rng, N, 25, resampling="multinomial")
+        _compare(_engine("lgss", ctas_per_filter=G), "lgss", theta, obs, N, 5, draws, resampling="multinomial")
+
+
+def test_multinomial_philox_path_replayed_through_oracle():
+    rng = np.random.default_rng(29)
+    theta = np.array([0.2, 0.5, 1.0, 0.5])
+    N, T, L, seed, ev = 5003, 20, 4, 77, 3
+    obs = _synthetic_obs("lgss", theta, T, rng)
+    eng = _engine("lgss")
+    z = np.zeros((T + 1, N))
+    u = np.zeros((T + 1, N))
+    for t in range(1, T + 1):
+        z[t] = eng.philox_normals(seed, ev, t, N)
+        u[t] = eng.philox_uniforms(seed, ev, t, N)
+    draws = orc.Draws(eng.philox_normals(seed, ev, 0, N), u, z, eng.philox_uniforms(seed, ev, -1)[0])
+    out = eng.run(obs, theta, N, L, True, True, 0.0, "multinomial", seed=seed, eval_ids=[ev], store_history=True)
+    hist = eng.fetch_history()
+    ref = orc.smoother(orc.MODEL_LGSS, theta, obs, N, L, draws, resampling="multinomial")
+    np.testing.assert_array_equal(hist["ancestors"][0], ref["ancestors"])
+    assert abs(out["log_like"][0] - ref["log_like"]) <= RTOL * abs(ref["log_like"])
+    ring = eng.run(obs, theta, N, L, True, True, 0.0, "multinomial", seed=seed, eval_ids=[ev])
+    np.testing.assert_array_equal(ring["smo"], out["smo"])
 
 
 def test_fixed_initial_state_and_degenerate_weights():

@@ -22,7 +22,7 @@ def _model_for(g):
     return model
 
 
-@pytest.mark.parametrize("name", [n for n in gu.golden_names() if "multinomial" not in n])
+@pytest.mark.parametrize("name", gu.golden_names())
 def test_estimator_results_match_reference(name):
     g = gu.load(name)
     model = _model_for(g)
