@@ -12,6 +12,9 @@
 #ifndef PFB_ITEMS_ALT
 #define PFB_ITEMS_ALT 9
 #endif
+#ifndef PFB_SMOOTH_THREADS
+#define PFB_SMOOTH_THREADS 128  // one warpgroup of smoother warps next to the PFB_BLOCK filter threads
+#endif
 #ifndef PFB_ITEMS_SMALL
 #define PFB_ITEMS_SMALL 2  // small filters (<= 1024 particles per CTA): no masked work on empty items
 #endif

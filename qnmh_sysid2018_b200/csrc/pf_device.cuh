@@ -392,6 +392,28 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// CTA-scope flags in shared memory (filter warps <-> smoother warps of one CTA)
+__device__ __forceinline__ unsigned ld_acquire_cta_shared_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// named barriers: the filter warps and the smoother warps of a CTA synchronise separately
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+template <int ID, int COUNT>
+__device__ __forceinline__ bool named_sync_or(bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+      : "=r"(r) : "r"((int)pred), "n"(ID), "n"(COUNT) : "memory");
+  return r != 0;
+}
 // system-scope variants for the exchange between the GPUs of a distributed filter (peer memory)
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   unsigned v;

@@ -59,6 +59,8 @@ struct DeviceProblem {
   double initial_state;
   unsigned long long seed;
   long long spin_limit;
+  unsigned sjobs0;    // smoother jobs completed per CTA before this launch (distributed filter: the peer
+                      // counters keep counting across launches; 0 otherwise)
   unsigned long long pol_keep, pol_once;  // L2 cache policies (evict_last / evict_first), created once per handle
   const double* obs;
   const double* consts;              // [B][kNumConsts]
@@ -100,6 +102,9 @@ struct PfKernel {
   static constexpr int kChunk = BLOCK * ITEMS;  // parents per scan sub-chunk (ITEMS odd: the
                                                 // thread-blocked smem pass is bank-conflict free)
   static constexpr int kWarps = BLOCK / 32;
+  static constexpr int kSmootherThreads = PFB_SMOOTH_THREADS;
+  static constexpr int kSmootherWarps = kSmootherThreads / 32;
+  static constexpr int kChase = 14;  // lineages per smoother thread in flight during the walk
   static constexpr int kRedK = kMaxParams + 2;
   static constexpr bool kFA = is_fully_adapted(MODEL);  // weights of generation t look ahead to y_{t+1}
 
@@ -109,12 +114,16 @@ struct PfKernel {
   double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
   unsigned short* sh_anc;  // [RA][anc_stride] shared-memory ancestor ring (anc_smem mode)
+  double* sh_m;        // [4] max log-weight of the last generations (filter -> smoother warps)
+  double* sh_sred;     // [kSmootherWarps][kMaxParams + 1] smoother reduction scratch
+  unsigned* sh_flags;  // [0] sequence number of the last complete generation, [1] smoother jobs done (G == 1)
   const int tid, lane, warp, g_loc, q, g;  // g: CTA index inside the (possibly multi-GPU) group
   const bool dist;                         // several GPUs work on this filter
   const int lo;                            // first global particle index held by this rank
   const bool pow2N;
   const double invN;
   unsigned epoch;
+  unsigned sjobs;  // smoother jobs of this CTA issued so far (both roles count them identically)
   bool aborted;
   int sx = 0, sw = 0, sa = 0;  // ring slots of the generation being written (t mod RX / RW / RA)
 #ifdef PFB_PROFILE
@@ -122,13 +131,22 @@ struct PfKernel {
   long long prof_t = 0;
 #endif
 
-  __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst)
+  __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst, double* shm,
+                      double* sred, unsigned* flags)
       : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst),
-        sh_anc(reinterpret_cast<unsigned short*>(smem + prob.tile_cap + (prob.G > 1 ? prob.G : 1))), tid(threadIdx.x),
+        sh_anc(reinterpret_cast<unsigned short*>(smem + prob.tile_cap + (prob.G > 1 ? prob.G : 1))),
+        sh_m(shm), sh_sred(sred), sh_flags(flags), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g_loc(blockIdx.x % prob.G_loc),
         q(blockIdx.x / prob.G_loc), g(prob.rank * prob.G_loc + blockIdx.x % prob.G_loc),
         dist(GENERAL && prob.R > 1), lo(prob.rank * prob.span), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
-        epoch(prob.epoch0), aborted(false) {}
+        epoch(prob.epoch0), sjobs(prob.sjobs0), aborted(false) {}
+
+  // barrier of the BLOCK filter threads (the smoother warps of the CTA do not take part)
+  static __device__ __forceinline__ void fsync() { named_sync<1, BLOCK>(); }
+  static __device__ __forceinline__ bool fsync_or(bool pred) { return named_sync_or<1, BLOCK>(pred); }
+  // barrier of the smoother warps
+  static __device__ __forceinline__ void ssync() { named_sync<2, kSmootherThreads>(); }
+  static __device__ __forceinline__ bool ssync_or(bool pred) { return named_sync_or<2, kSmootherThreads>(pred); }
 
   // ---- inter-CTA exchange (all-gather of one double per CTA + group barrier).  Arrival is a
   //      release-increment of one counter per group; ONE thread per CTA polls it (G pollers on one
@@ -137,12 +155,12 @@ struct PfKernel {
   __device__ void exchange_arrive(double v) {
     const int G = p.G;
     if (G == 1) {
-      __syncthreads();
+      fsync();
       if (tid == 0) sh_x[0] = v;
       return;
     }
     ++epoch;
-    __syncthreads();  // all global writes of this CTA precede the release below
+    fsync();  // all global writes of this CTA precede the release below
     if (dist) {
       // all-gather across GPUs: write the value into every rank's buffer and release-increment
       // every rank's counter at system scope (NVLink peer stores); thread r serves rank r
@@ -158,29 +176,72 @@ struct PfKernel {
 
   // second half: waits until every CTA of the group has arrived; sh_x[0..G) then holds all values.
   // Independent work placed between arrive and wait overlaps the exchange latency and the skew.
-  __device__ void exchange_wait() {
+  // `s_target` > 0: additionally wait until the smoother warps of every CTA of the group have
+  // completed their first s_target jobs (their reads of the ring slots the next phase overwrites).
+  __device__ void exchange_wait(unsigned s_target = 0) {
     const int G = p.G;
     if (G == 1) {
-      __syncthreads();
+      int ab1 = 0;
+      if (s_target != 0 && tid == 0) ab1 = wait_counter<0>(sh_flags + 1, s_target);
+      if (s_target != 0) aborted = fsync_or(ab1);
+      else fsync();
       return;
     }
     const double* val = p.xval + ((size_t)q * 2 + (epoch & 1u)) * G;
     const unsigned* cnt = p.xcount + (size_t)q * 32;
     int ab = 0;
     if (tid == 0) {
-      const unsigned target = epoch * (unsigned)G;
-      long long spins = 0;
-      while ((int)((dist ? ld_acquire_sys_u32(cnt) : ld_acquire_u32(cnt)) - target) < 0) {
-        if ((++spins & 1023) == 0 && (spins > p.spin_limit || ld_relaxed_i32(p.abort_flag) != 0)) {
-          atomicExch(p.abort_flag, 1);
-          ab = 1;
-          break;
-        }
+      ab = dist ? wait_counter<2>(cnt, epoch * (unsigned)G) : wait_counter<1>(cnt, epoch * (unsigned)G);
+      if (!ab && s_target != 0)
+        ab = dist ? wait_counter<2>(cnt + 16, s_target * (unsigned)G) : wait_counter<1>(cnt + 16, s_target * (unsigned)G);
+    }
+    aborted = fsync_or(ab);  // block-uniform; orders the reads below after the acquire
+    for (int i = tid; i < G; i += BLOCK) sh_x[i] = ld_cg(val + i);
+    fsync();
+  }
+
+  // one thread spins until *cnt >= target (wrap-safe); SCOPE 0: CTA flag in shared memory, 1: GPU,
+  // 2: system (peer GPUs).  Returns 1 when the wait was abandoned (spin limit / abort flag).
+  template <int SCOPE>
+  __device__ int wait_counter(const unsigned* cnt, unsigned target) const {
+    long long spins = 0;
+    for (;;) {
+      const unsigned v = SCOPE == 0 ? ld_acquire_cta_shared_u32(cnt) : (SCOPE == 1 ? ld_acquire_u32(cnt) : ld_acquire_sys_u32(cnt));
+      if ((int)(v - target) >= 0) return 0;
+      if (SCOPE == 0) __nanosleep(32);
+      if ((++spins & 1023) == 0 && (spins > p.spin_limit || ld_relaxed_i32(p.abort_flag) != 0)) {
+        atomicExch(p.abort_flag, 1);
+        return 1;
       }
     }
-    aborted = __syncthreads_or(ab) != 0;  // block-uniform; orders the reads below after the acquire
-    for (int i = tid; i < G; i += BLOCK) sh_x[i] = ld_cg(val + i);
-    __syncthreads();
+  }
+
+  // ---- filter warps -> smoother warps of the same CTA: generation `seq` is complete everywhere
+  //      (this CTA has passed the group barrier that follows its children) and its max log-weight
+  __device__ void publish_generation(unsigned seq, int tau, double m) {
+    if (tid == 0) {
+      sh_m[tau & 3] = m;
+      st_release_cta_shared_u32(sh_flags, seq);
+    }
+  }
+
+  // ---- smoother warps: wait for a generation / report a finished job
+  __device__ bool smoother_wait_generation(unsigned seq) {
+    int ab = 0;
+    if (tid == BLOCK) ab = wait_counter<0>(sh_flags, seq);
+    return ssync_or(ab);
+  }
+  __device__ void smoother_job_done() {
+    ++sjobs;
+    ssync();  // every smoother thread has finished reading the rings for this job
+    const int st = tid - BLOCK;
+    if (p.G == 1) {
+      if (st == 0) st_release_cta_shared_u32(sh_flags + 1, sjobs);
+    } else if (dist) {
+      if (st < p.R) red_release_sys_add_u32(p.peer_xcount[st] + 16, 1u);
+    } else if (st == 0) {
+      red_release_add_u32(p.xcount + (size_t)q * 32 + 16, 1u);
+    }
   }
 
   __device__ void exchange(double v) {
@@ -237,9 +298,9 @@ struct PfKernel {
   __device__ double block_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
+    fsync();
     if (lane == 0) sh_red[warp] = v;
-    __syncthreads();
+    fsync();
     double r = (lane < kWarps) ? sh_red[lane] : -INFINITY;  // every warp reduces the same values
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r = dmax(r, __shfl_xor_sync(0xffffffffu, r, o));
@@ -250,9 +311,9 @@ struct PfKernel {
   // block_max
   __device__ double block_sum1(double v) {
     v = warp_sum(v);
-    __syncthreads();
+    fsync();
     if (lane == 0) sh_red[warp] = v;
-    __syncthreads();
+    fsync();
     const double r = (lane < kWarps) ? sh_red[lane] : 0.0;
     return warp_sum(r);
   }
@@ -263,39 +324,39 @@ struct PfKernel {
   __device__ void block_sum(double (&v)[K]) {
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
+    fsync();
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k) sh_red[k * 32 + warp] = v[k];
     }
-    __syncthreads();
+    fsync();
     if (warp < K) {
       double r = (lane < kWarps) ? sh_red[warp * 32 + lane] : 0.0;
       r = warp_sum(r);
       if (lane == 0) sh_red[8 * 32 + warp] = r;
     }
-    __syncthreads();
+    fsync();
     if (tid == 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k) v[k] = sh_red[8 * 32 + k];
     }
-    __syncthreads();
+    fsync();
   }
 
   __device__ int block_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     int* red = reinterpret_cast<int*>(sh_red);
-    __syncthreads();
+    fsync();
     if (lane == 0) red[warp] = v;
-    __syncthreads();
+    fsync();
     int r = 0;
     if (warp == 0) {
       for (int i = lane; i < kWarps; i += 32) r += red[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     }
-    __syncthreads();
+    fsync();
     return r;  // valid in warp 0
   }
 
@@ -318,7 +379,7 @@ struct PfKernel {
       tile[jl] = s;
     }
     if (accF) *accF += f;
-    __syncthreads();
+    fsync();
   }
 
   // ---- in-place inclusive scan of tile[0..kChunk): thread-blocked runs, warp shuffle scan of the
@@ -329,7 +390,7 @@ struct PfKernel {
     for (int k = 0; k < ITEMS; ++k) run += tile[tid * ITEMS + k];
     const double incl = warp_inclusive_scan(run, lane);
     if (lane == 31) sh_red[warp] = incl;
-    __syncthreads();
+    fsync();
     double w = (lane < kWarps) ? sh_red[lane] : 0.0;  // every warp scans the warp totals itself
     const double wi = warp_inclusive_scan(w, lane);
     const double woff = __shfl_sync(0xffffffffu, wi - w, warp);
@@ -340,14 +401,16 @@ struct PfKernel {
       r += tile[tid * ITEMS + k];
       tile[tid * ITEMS + k] = r;
     }
-    __syncthreads();
+    fsync();
     return total;
   }
 
-  // ---- fixed-lag smoother increment for smoothing time i with weights of generation tau
-  //      (standard.py:146-169).  The weights s[j] = exp(logw_tau[j] - m_tau) are recomputed from
-  //      the log-weight ring, so the job only reads data that is final and can run while the CTA
-  //      waits for an exchange.
+  // ---- fixed-lag smoother (standard.py:146-169), run by the smoother warps of the CTA while the
+  //      filter warps go on with the next time steps.  A job takes the weights of generation tau
+  //      (s[j] = exp(logw_tau[j] - m_tau), recomputed from the log-weight ring), walks every lineage
+  //      of this CTA's index range back to smoothing time i and accumulates s * (x_i, grad log p).
+  //      It only reads generations that are complete; the filter warps wait for it (exchange_wait)
+  //      before they overwrite the ring slots it reads.
   // element n (global index) of ring row `slot`: own memory, or the owner rank's memory over NVLink
   template <typename T>
   __device__ __forceinline__ T ld_ring(const T* local_row_view, T* const* peer_base, int slot, int n,
@@ -371,22 +434,22 @@ struct PfKernel {
     return s < 0 ? s + R : s;
   }
 
-  // lineages of generation tau (ancestor-ring slot `slot_a`) walked back `nlev` generations to
-  // smoothing time i (state-ring slot `si`)
-  template <int NI>
-  __device__ void smooth_chunk(const Real* lw, double m_tau, const Real* xr, const int* ar,
-                               const double* obs, int nlev, int slot_a, int si, int i, int c0, int len,
+  // lineages [c0, c0 + len) of generation tau (ancestor-ring slot `slot_a`) walked back `nlev`
+  // generations to smoothing time i (state-ring slot `si`); len <= kChase * kSmootherThreads
+  __device__ void smooth_round(const Real* lw, double m_tau, const Real* xr, const int* ar, double y,
+                               int nlev, int slot_a, int si, int c0, int len,
                                double (&acc)[kMaxParams + 1]) {
+    constexpr int ST = kSmootherThreads;
+    const int st = tid - BLOCK;
     const size_t NS = (size_t)p.NS;
     const uint64_t keep = p.pol_keep, once = p.pol_once;
-    int cur[NI], nxt[NI];
-    Real l[NI];
+    const int kmax = (len + ST - 1) / ST;  // block-uniform number of live items
+    int cur[kChase], nxt[kChase];
 #pragma unroll
-    for (int k = 0; k < NI; ++k) {
-      const int jl = k * BLOCK + tid;
+    for (int k = 0; k < kChase; ++k) {
+      const int jl = k * ST + st;
       cur[k] = (jl < len) ? c0 + jl : c0;
       nxt[k] = cur[k];
-      l[k] = (jl < len) ? ld_hint(lw + c0 + jl, once) : (Real)(-INFINITY);
     }
     // nlev - 1 hops to the ancestors at time i+1, then one more to time i
     int slot = slot_a;
@@ -394,87 +457,131 @@ struct PfKernel {
       for (int lvl = 1; lvl < nlev; ++lvl) {
         const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
-        for (int k = 0; k < NI; ++k) cur[k] = row[cur[k]];
+        for (int k = 0; k < kChase; ++k)
+          if (k < kmax) cur[k] = row[cur[k]];
         slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
       if (nlev > 0) {
         const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
-        for (int k = 0; k < NI; ++k) {
+        for (int k = 0; k < kChase; ++k) {
           nxt[k] = cur[k];
-          cur[k] = row[cur[k]];
+          if (k < kmax) cur[k] = row[cur[k]];
         }
       }
     } else {
       for (int lvl = 1; lvl < nlev; ++lvl) {
         const int* a = opaque(ar + (size_t)slot * NS);
 #pragma unroll
-        for (int k = 0; k < NI; ++k) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+        for (int k = 0; k < kChase; ++k)
+          if (k < kmax) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
         slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
       if (nlev > 0) {
         const int* a = opaque(ar + (size_t)slot * NS);
 #pragma unroll
-        for (int k = 0; k < NI; ++k) {
+        for (int k = 0; k < kChase; ++k) {
           nxt[k] = cur[k];
-          cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+          if (k < kmax) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
         }
       }
     }
     const int sn = (si + 1 == p.RX) ? 0 : si + 1;
     const Real* xi = opaque(xr + (size_t)si * NS);
     const Real* xn = opaque(xr + (size_t)sn * NS);
-    const double y = __ldg(obs + i);
-    Real xc[NI], xnext[NI];
+    // states and weights in two halves (register budget), accumulated in item order
+    constexpr int kHalf = kChase / 2;
 #pragma unroll
-    for (int k = 0; k < NI; ++k) {
-      xc[k] = ld_ring<Real>(xi, reinterpret_cast<Real* const*>(p.peer_x), si, cur[k], once);
-      xnext[k] = ld_ring<Real>(xn, reinterpret_cast<Real* const*>(p.peer_x), sn, nxt[k], once);
-    }
+    for (int h = 0; h < 2; ++h) {
+      if (h * kHalf >= kmax) break;
+      Real l[kHalf], xc[kHalf], xnext[kHalf];
 #pragma unroll
-    for (int k = 0; k < NI; ++k) {
-      const int jl = k * BLOCK + tid;
-      const Real xck = xc[k], xnk = xnext[k];
-      const double sw = (jl < len) ? shifted_weight<Real>(l[k], m_tau) : 0.0;
-      double gr[kMaxParams];
-      Ops::gradient(sh_c, xnk, xck, y, gr);
-      const double t0 = (double)xck * sw;
-      // np.nansum: NaN terms are skipped.  A term can only be NaN when a state is not finite.
-      if (isfinite((double)xck) && isfinite((double)xnk)) {
-        acc[0] += t0;
+      for (int k = 0; k < kHalf; ++k) {
+        const int kk = h * kHalf + k;
+        const int jl = kk * ST + st;
+        l[k] = (jl < len) ? ld_hint(lw + (unsigned)(c0 + jl), once) : (Real)(-INFINITY);
+        xc[k] = ld_ring<Real>(xi, reinterpret_cast<Real* const*>(p.peer_x), si, cur[kk], once);
+        xnext[k] = ld_ring<Real>(xn, reinterpret_cast<Real* const*>(p.peer_x), sn, nxt[kk], once);
+      }
 #pragma unroll
-        for (int pp = 0; pp < kMaxParams; ++pp) acc[1 + pp] += gr[pp] * sw;
-      } else {
-        if (!isnan(t0)) acc[0] += t0;
+      for (int k = 0; k < kHalf; ++k) {
+        const int jl = (h * kHalf + k) * ST + st;
+        const Real xck = xc[k], xnk = xnext[k];
+        const double sw = (jl < len) ? shifted_weight<Real>(l[k], m_tau) : 0.0;
+        double gr[kMaxParams];
+        Ops::gradient(sh_c, xnk, xck, y, gr);
+        const double t0 = (double)xck * sw;
+        // np.nansum: NaN terms are skipped.  A term can only be NaN when a state is not finite.
+        if (isfinite((double)xck) && isfinite((double)xnk)) {
+          acc[0] += t0;
 #pragma unroll
-        for (int pp = 0; pp < kMaxParams; ++pp) {
-          const double tp = gr[pp] * sw;
-          if (!isnan(tp)) acc[1 + pp] += tp;
+          for (int pp = 0; pp < kMaxParams; ++pp) acc[1 + pp] += gr[pp] * sw;
+        } else {
+          if (!isnan(t0)) acc[0] += t0;
+#pragma unroll
+          for (int pp = 0; pp < kMaxParams; ++pp) {
+            const double tp = gr[pp] * sw;
+            if (!isnan(tp)) acc[1 + pp] += tp;
+          }
         }
       }
     }
   }
 
-  // smoother increment of lag time `tau` over the sub-chunks [c_lo, c_hi) of this CTA's range
-  __device__ void smooth_job(const Real* lwr, double m_tau, const Real* xr, const int* ar,
-                             const double* obs, int tau, int j_begin, int j_end, int c_lo, int c_hi,
-                             double (&acc)[kMaxParams + 1]) {
-    // tau = t - 2 relative to the generation being written
-    const Real* lw = lwr + (size_t)ring_back(sw, 2, p.RW) * p.NS;
-    const int slot_a = ring_back(sa, 2, p.RA), si = ring_back(sx, p.L + 2, p.RX);
-    constexpr int SB = (PFB_SMOOTH_BATCH > 0 && PFB_SMOOTH_BATCH < ITEMS) ? PFB_SMOOTH_BATCH : ITEMS;
-    const int first = j_begin + c_lo * kChunk;
-    const int last = min(j_end, j_begin + c_hi * kChunk);
-    for (int c0 = first; c0 < last; c0 += SB * BLOCK)
-      smooth_chunk<SB>(lw, m_tau, xr, ar, obs, p.L, slot_a, si, tau - p.L, c0, min(SB * BLOCK, last - c0), acc);
+  // one smoothing time: all lineages of this CTA's range, block sum, partial written for finalize
+  __device__ void smooth_time(int b, const Real* lwr, double m_tau, const Real* xr, const int* ar,
+                              const double* obs, int tau, int i, int j_begin, int j_end) {
+    const int st = tid - BLOCK;
+    const int swarp = st >> 5;
+    const Real* lw = lwr + (size_t)(tau % p.RW) * p.NS;
+    const int slot_a = tau % p.RA, si = i % p.RX;
+    const double y = __ldg(obs + i);
+    double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    constexpr int kRound = kChase * kSmootherThreads;
+    for (int c0 = j_begin; c0 < j_end; c0 += kRound)
+      smooth_round(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
+#pragma unroll
+    for (int k = 0; k <= kMaxParams; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k <= kMaxParams; ++k) sh_sred[swarp * (kMaxParams + 1) + k] = acc[k];
+    }
+    ssync();
+    if (st == 0) {
+      double* dst = p.smo_part + (((size_t)b * (p.T + 1) + i) * p.G_loc + g_loc) * (p.P + 1);
+      for (int k = 0; k <= p.P; ++k) {
+        double r = 0.0;
+        for (int w = 0; w < kSmootherWarps; ++w) r += sh_sred[w * (kMaxParams + 1) + k];  // fixed order
+        dst[k] = r;
+      }
+    }
+    ssync();  // sh_sred may be rewritten
   }
 
-  __device__ void write_smooth_partials(int b, int i, double (&acc)[kMaxParams + 1]) {
-    block_sum(acc);
-    if (tid == 0) {
-      double* dst = p.smo_part + (((size_t)b * (p.T + 1) + i) * p.G_loc + g_loc) * (p.P + 1);
-      for (int k = 0; k <= p.P; ++k) dst[k] = acc[k];
+  // all smoother jobs of filter evaluation b (the b_idx-th evaluation of this CTA): lag times
+  // tau = L .. T-1 smooth time tau - L as soon as generation tau is complete; lag time T serves the
+  // last L smoothing times (standard.py:146: lag = min(i + L, T))
+  __device__ void run_smoother(int b, int b_idx) {
+    const int N = p.N, T = p.T, L = p.L;
+    const int ws = p.ws_per_filter ? b : q;
+    const size_t NS = (size_t)p.NS;
+    const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS - lo;
+    const Real* lwr = reinterpret_cast<const Real*>(p.logw) + (size_t)ws * p.RW * NS - lo;
+    const int* ar = p.anc_ring + (size_t)ws * p.RA * NS - lo;
+    const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
+    const int j_begin = min(g * p.per_cta, N);
+    const int j_end = min(j_begin + p.per_cta, N);
+    const unsigned seq0 = (unsigned)b_idx * (unsigned)(T + 2) + 1u;  // generation tau <-> seq0 + tau
+    for (int tau = L; tau < T; ++tau) {
+      if (smoother_wait_generation(seq0 + (unsigned)tau)) { aborted = true; return; }
+      smooth_time(b, lwr, sh_m[tau & 3], xr, ar, obs, tau, tau - L, j_begin, j_end);
+      smoother_job_done();
     }
+    if (smoother_wait_generation(seq0 + (unsigned)T)) { aborted = true; return; }
+    const double m_T = sh_m[T & 3];
+    for (int i = T - 1; i >= ((T - L > 0) ? T - L : 0); --i)
+      smooth_time(b, lwr, m_T, xr, ar, obs, T, i, j_begin, j_end);
+    smoother_job_done();
   }
 
   // position of child n on the unit interval (resampling.pyx:72 systematic, :51 stratified)
@@ -693,7 +800,7 @@ struct PfKernel {
   static __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }
 
   // ---- one filter evaluation (all T steps) -------------------------------------------------
-  __device__ void run_filter(int b) {
+  __device__ void run_filter(int b, int b_idx) {
     const int N = p.N, T = p.T, L = p.L;
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
@@ -710,9 +817,9 @@ struct PfKernel {
     const double* inj_u = (GENERAL && p.inject) ? p.inj_u + ib * (T + 1) * u_row : nullptr;
     const double* inj_z = (GENERAL && p.inject) ? p.inj_z + ib * (size_t)(T + 1) * N : nullptr;
 
-    __syncthreads();
+    fsync();
     if (tid < kNumConsts) sh_c[tid] = p.consts[(size_t)b * kNumConsts + tid];
-    __syncthreads();
+    fsync();
 
     const int j_begin = min(g * p.per_cta, N);
     const int j_end = min(j_begin + p.per_cta, N);
@@ -744,7 +851,10 @@ struct PfKernel {
     exchange(block_max(mx0));
     sx = sw = sa = 0;  // generation 0 lives in slot 0 of every ring
     double m = xchg_max();
-    double m_prev = m;  // max log-weight of generation tau-1 (for the deferred smoother job)
+    // smoother bookkeeping: generation tau <-> sequence number seq0 + tau; jobs of this evaluation
+    const unsigned seq0 = (unsigned)b_idx * (unsigned)(T + 2) + 1u;
+    const int n_reg_jobs = (p.do_smoother && T > L) ? T - L : 0;  // lag times L .. T-1
+    publish_generation(seq0, 0, m);
 
     for (int t = 1; t <= T + 1; ++t) {
       if (aborted) return;
@@ -755,12 +865,11 @@ struct PfKernel {
       sw = (sw + 1 == p.RW) ? 0 : sw + 1;
       sa = (sa + 1 == p.RA) ? 0 : sa + 1;
       const bool final_step = (t == T + 1);
-      // Deferred smoother job of this step: lag time tau-1 (its weights, ancestors and states are
-      // final), split over the two exchange waits.  Lag time T is handled by the tail below.
-      const int tau_sm = tau - 1;
-      const bool job = p.do_smoother && tau_sm >= L;
-      const int c_half = PFB_SMOOTH_SPLIT ? (n_chunks + 1) / 2 : n_chunks;
-      double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      // Phase B of this step overwrites the ring slots of generation t-3 (log-weights), t-L-2
+      // (ancestors) and t-L-3 (states): the smoother jobs of lag times <= t-3 must be complete on
+      // every CTA of the group first (they run on the smoother warps, up to two steps behind).
+      const int jobs_needed = min(max(t - 2 - L, 0), n_reg_jobs);
+      const unsigned s_target = jobs_needed > 0 ? sjobs + (unsigned)jobs_needed : 0u;
 
       // per-step scalars, issued early so that their latency hides behind phase A
       double u = 0.0, y_prop = 0.0, y_obs = 0.0;
@@ -803,9 +912,8 @@ struct PfKernel {
       }
       PFB_TICK(1);
       exchange_arrive(A);
-      if (job) smooth_job(lwr, m_prev, xr, ar, obs, tau_sm, j_begin, j_end, 0, final_step ? n_chunks : c_half, acc);
       PFB_TICK(9);
-      exchange_wait();
+      exchange_wait(s_target);
       PFB_TICK(2);
       // prefix over the group + this CTA's children range, evaluated by every warp on its own
       // (lanes 0 / 1 take the two boundaries side by side): no block barrier on the critical path
@@ -824,20 +932,6 @@ struct PfKernel {
       if (g_loc == 0 && tid == 0) {
         p.stat_m[(size_t)b * (T + 1) + tau] = m;
         p.stat_S[(size_t)b * (T + 1) + tau] = S;
-      }
-
-      // ---------------- smoother tail (standard.py:146: lag = T for the last L times)
-      if (final_step && p.do_smoother) {
-        if (job) write_smooth_partials(b, tau_sm - L, acc);  // the deferred job of lag time T-1
-        const int i_first = (T - L > 0) ? T - L : 0;
-        for (int i = T - 1; i >= i_first; --i) {
-          double ta[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
-          for (int c = 0; c < n_chunks; ++c) {
-            const int c0 = j_begin + c * kChunk;
-            smooth_chunk<ITEMS>(lw_prev, m, xr, ar, obs, tau - i, ring_back(sa, 1, p.RA), ring_back(sx, T + 1 - i, p.RX), i, c0, min(kChunk, j_end - c0), ta);
-          }
-          write_smooth_partials(b, i, ta);
-        }
       }
 
       // ---------------- phase B
@@ -860,7 +954,7 @@ struct PfKernel {
           }
           base += sh_red[264 + c];
         }
-        __syncthreads();
+        fsync();
         if (final_step) {
           // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
           for (int jl = tid; jl < own; jl += BLOCK)
@@ -878,7 +972,7 @@ struct PfKernel {
         for (int c = 0; c < n_chunks; ++c) {
           const int c0 = j_begin + c * kChunk;
           const int len = min(kChunk, j_end - c0);
-          __syncthreads();
+          fsync();
           load_chunk(sh_s, lw_prev, x_prev, c0, len, m, nullptr);
           chunk_total = scan_chunk(sh_s);
 #pragma unroll
@@ -886,7 +980,7 @@ struct PfKernel {
             const int jl = k * BLOCK + tid;
             if (jl < len) sh_s[jl] = __dmul_rn(__dadd_rn(base, sh_s[jl]), invS);
           }
-          __syncthreads();
+          fsync();
           if (final_step) {
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
@@ -924,7 +1018,12 @@ struct PfKernel {
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);
         if (tid == 0 && cnt) atomicAdd(p.traj_k + b, cnt);
-        exchange(0.0);  // all counts are in; also fences the workspace before the next filter
+        // all counts are in; every smoother job of this evaluation is complete on every CTA (the next
+        // evaluation reuses the rings)
+        const unsigned jobs_total = p.do_smoother ? (unsigned)n_reg_jobs + 1u : 0u;
+        exchange_arrive(0.0);
+        exchange_wait(jobs_total ? sjobs + jobs_total : 0u);
+        sjobs += jobs_total;
         if (g_loc == 0 && tid == 0) {
           int k = ld_cg(p.traj_k + b);
           if (k > N - 1) k = N - 1;
@@ -937,29 +1036,50 @@ struct PfKernel {
         mx = block_max(mx);
         PFB_TICK(5);
         exchange_arrive(mx);
-        if (job) {
-          smooth_job(lwr, m_prev, xr, ar, obs, tau_sm, j_begin, j_end, c_half, n_chunks, acc);
-          write_smooth_partials(b, tau_sm - L, acc);
-        }
         PFB_TICK(10);
         exchange_wait();
         PFB_TICK(6);
-        m_prev = m;
         m = xchg_max();
+        publish_generation(seq0 + (unsigned)t, t, m);
         PFB_TICK(7);
       }
     }
   }
 };
 
+// Warp-specialised CTA: BLOCK filter threads (time-critical particle-filter loop) followed by one
+// warpgroup of smoother threads (fixed-lag lineage walks, up to two time steps behind).  The register
+// file is re-split after launch (setmaxnreg): 96 per thread at launch -> 88 for the filter warps,
+// 128 for the smoother warps (BLOCK * 88 + 128 * 128 = (BLOCK + 128) * 96 for BLOCK = 512).
 template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB, bool GENERAL>
-__global__ void __launch_bounds__(BLOCK, MINB) pf_persistent_kernel(const DeviceProblem prob) {
+__global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_kernel(const DeviceProblem prob) {
+  static_assert(BLOCK == 512 && PFB_SMOOTH_THREADS == 128, "the setmaxnreg split below assumes 512 + 128 threads");
   extern __shared__ double pf_smem[];
   __shared__ double sh_red[9 * 32 + 8];
   __shared__ double sh_c[kNumConsts];
-  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c);
-  for (int b = k.q; b < prob.B; b += prob.n_groups) {
-    k.run_filter(b);
+  __shared__ double sh_m[4];
+  __shared__ double sh_sred[(PFB_SMOOTH_THREADS / 32) * (kMaxParams + 1)];
+  __shared__ unsigned sh_flags[4];
+  if (threadIdx.x == 0) {
+    sh_flags[0] = 0u;
+    sh_flags[1] = prob.sjobs0;
+  }
+  __syncthreads();
+  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c, sh_m, sh_sred, sh_flags);
+  if (threadIdx.x >= BLOCK) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    if (!prob.do_smoother) return;
+    int b_idx = 0;
+    for (int b = k.q; b < prob.B; b += prob.n_groups, ++b_idx) {
+      k.run_smoother(b, b_idx);
+      if (k.aborted) return;
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+  int b_idx = 0;
+  for (int b = k.q; b < prob.B; b += prob.n_groups, ++b_idx) {
+    k.run_filter(b, b_idx);
     if (k.aborted) return;
   }
 #ifdef PFB_PROFILE

@@ -72,7 +72,8 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-constexpr int kBlock = PFB_BLOCK;
+constexpr int kBlock = PFB_BLOCK;                       // filter threads per CTA
+constexpr int kThreads = PFB_BLOCK + PFB_SMOOTH_THREADS;  // + the smoother warpgroup
 constexpr int kItems = PFB_ITEMS;        // default tile granularity
 constexpr int kItemsAlt = PFB_ITEMS_ALT;  // alternative, chosen when it saves a scan sub-chunk
 constexpr int kItemsSmall = PFB_ITEMS_SMALL;  // small filters: a CTA's parent range fits 2 per thread
@@ -158,6 +159,7 @@ struct pfb200_handle {
   long long opt_dist_world = 1, opt_dist_rank = 0;
   bool dist_connected = false;
   unsigned dist_epoch = 0;
+  unsigned dist_sjobs = 0;
   void* peer_opened[8][5] = {};  // IPC mappings to close
   // configured problem
   bool configured = false;
@@ -384,7 +386,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     for (int pass = 0; pass < 3; ++pass) {
       // shared memory of the current guess -> co-resident CTAs -> group size
       smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
       if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
       capacity = bps * h->num_sms;
       if (h->opt_ctas_per_filter > 0) G_loc = (int)h->opt_ctas_per_filter;
@@ -416,7 +418,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const bool anc_smem = h->opt_anc_smem && G == 1 && R == 1 && !history && do_smoother && N <= 65535 &&
                         (size_t)(tile_cap + 1) * sizeof(double) + anc_bytes <= smem_limit;
   smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes : 0);
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kBlock, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
   capacity = bps * h->num_sms;
   if (G_loc > capacity)
@@ -439,7 +441,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
   p.N = N; p.NS = R > 1 ? G_loc * per : (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
-  p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0;
+  p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0; p.sjobs0 = 0;
   p.RX = history ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
   p.RA = history ? T + 1 : L + 2;
   p.RW = history ? T + 1 : 3;
@@ -549,12 +551,14 @@ int pfb200_execute(pfb200_handle* h) {
     if (!h->dist_connected) return fail(PFB200_ESTATE, "pfb200_execute: distributed filter is not connected (pfb200_dist_connect)");
     p.epoch0 = h->dist_epoch;               // peer counters keep counting across launches
     h->dist_epoch += 2u * (unsigned)p.T + 3u;  // exchanges per launch: init + 2 per step + 2 at the end
+    p.sjobs0 = h->dist_sjobs;               // smoother jobs per CTA and launch: lag times L..T-1 + the tail
+    if (p.do_smoother) h->dist_sjobs += (unsigned)(p.T > p.L ? p.T - p.L : 0) + 1u;
   } else {
     CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, (size_t)p.n_groups * 32 * 4, h->stream));
   }
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
-  const dim3 grid(p.n_groups * p.G_loc), block(kBlock);
+  const dim3 grid(p.n_groups * p.G_loc), block(kThreads);
   {
     // The ancestor ring is re-read every time step for L steps (fixed-lag lineage walks) while
     // particles and log-weights stream through: keep it resident in L2.
@@ -740,6 +744,7 @@ int pfb200_dist_export(pfb200_handle* h, void* out, int bytes) {
   // fresh counters; the caller synchronises all ranks (host barrier) between connect and execute
   CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
   h->dist_epoch = 0;
+  h->dist_sjobs = 0;
   return PFB200_OK;
 }
 
