@@ -34,6 +34,9 @@ namespace pfb200 {
 #define PFB_TICK(slot) do { } while (0)
 #endif
 constexpr int kProfSlots = 16;
+#ifndef PFB_CHASE
+#define PFB_CHASE 21
+#endif
 #ifndef PFB_SMOOTH_BATCH
 #define PFB_SMOOTH_BATCH 0  // lineages per thread in flight in the smoother job (0 = ITEMS)
 #endif
@@ -104,7 +107,9 @@ struct PfKernel {
   static constexpr int kWarps = BLOCK / 32;
   static constexpr int kSmootherThreads = PFB_SMOOTH_THREADS;
   static constexpr int kSmootherWarps = kSmootherThreads / 32;
-  static constexpr int kChase = 14;  // lineages per smoother thread in flight during the walk
+  static constexpr int kChase = PFB_CHASE;  // lineages per smoother thread in flight during the walk
+  static constexpr int kGather = 7;         // ... and per state/weight gather pass (register budget)
+  static_assert(kChase % kGather == 0, "the walk width is a multiple of the gather width");
   static constexpr int kRedK = kMaxParams + 2;
   static constexpr bool kFA = is_fully_adapted(MODEL);  // weights of generation t look ahead to y_{t+1}
 
@@ -489,10 +494,10 @@ struct PfKernel {
     const int sn = (si + 1 == p.RX) ? 0 : si + 1;
     const Real* xi = opaque(xr + (size_t)si * NS);
     const Real* xn = opaque(xr + (size_t)sn * NS);
-    // states and weights in two halves (register budget), accumulated in item order
-    constexpr int kHalf = kChase / 2;
+    // states and weights in passes of kGather items (register budget), accumulated in item order
+    constexpr int kHalf = kGather;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kChase / kGather; ++h) {
       if (h * kHalf >= kmax) break;
       Real l[kHalf], xc[kHalf], xnext[kHalf];
 #pragma unroll
