@@ -62,6 +62,9 @@ struct DeviceProblem {
   double initial_state;
   unsigned long long seed;
   long long spin_limit;
+  int halo;           // distributed filter: every ring row is [halo | own span | halo]: a rank mirrors the
+                      // `halo` nearest states and ancestors of both neighbours, so that lineage walks
+                      // across a rank boundary stay in local memory (row stride NS = span + 2 * halo)
   unsigned sjobs0;    // smoother jobs completed per CTA before this launch (distributed filter: the peer
                       // counters keep counting across launches; 0 otherwise)
   unsigned long long pol_keep, pol_once;  // L2 cache policies (evict_last / evict_first), created once per handle
@@ -422,7 +425,89 @@ struct PfKernel {
                                        uint64_t pol) const {
     if (!dist || (unsigned)(n - lo) < (unsigned)p.span) return ld_hint(local_row_view + (unsigned)n, pol);  // n >= 0: one IMAD.WIDE.U32
     const int r = n / p.span;
-    return ld_sys(peer_base[r] + (size_t)slot * p.NS + (n - r * p.span));
+    return ld_sys(peer_base[r] + (size_t)slot * p.NS + p.halo + (n - r * p.span));
+  }
+
+  // DIST: is global particle n held in this rank's memory (own span or a halo mirror)?
+  __device__ __forceinline__ bool is_local(int n) const {
+    return (unsigned)(n - lo + p.halo) < (unsigned)(p.span + 2 * p.halo);
+  }
+  // row `slot` of rank r's ring as a global-index view (element n at view[n]; halos included)
+  template <typename T>
+  __device__ __forceinline__ T* peer_row(T* base, int r, int slot) const {
+    return base + (size_t)slot * p.NS + p.halo - (size_t)r * p.span;
+  }
+
+  // one hop of all live lineages of a thread.  DIST: lineages inside the rank or its halos are one
+  // batch of independent local loads; only when some lineage of the thread is far away the hop
+  // resolves peer addresses (again one batch, over NVLink).
+  template <bool DIST>
+  __device__ __forceinline__ void hop(int (&cur)[kChase], int kmax, const int* a, int slot, uint64_t keep) const {
+    bool far = false;
+    if (DIST) {
+#pragma unroll
+      for (int k = 0; k < kChase; ++k) far |= !is_local(cur[k]);
+    }
+    if (!DIST || !far) {
+#pragma unroll
+      for (int k = 0; k < kChase; ++k)
+        if (k < kmax) cur[k] = ld_hint(a + (unsigned)cur[k], keep);
+      return;
+    }
+    const int* ptr[kChase];
+#pragma unroll
+    for (int k = 0; k < kChase; ++k) {
+      const int n = cur[k];
+      ptr[k] = is_local(n) ? a + (unsigned)n : peer_row(p.peer_anc[n / p.span], n / p.span, slot) + n;
+    }
+#pragma unroll
+    for (int k = 0; k < kChase; ++k)
+      if (k < kmax) cur[k] = ld_sys(ptr[k]);
+  }
+
+  // state gathers of one pass: x_i[cur], x_{i+1}[nxt]
+  template <bool DIST, int NG>
+  __device__ __forceinline__ void gather_states(const Real* xi, const Real* xn, int si, int sn, const int* cur,
+                                                const int* nxt, Real (&xc)[NG], Real (&xnext)[NG], uint64_t once) const {
+    bool far = false;
+    if (DIST) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) far |= !is_local(cur[k]) || !is_local(nxt[k]);
+    }
+    if (!DIST || !far) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        xc[k] = ld_hint(xi + (unsigned)cur[k], once);
+        xnext[k] = ld_hint(xn + (unsigned)nxt[k], once);
+      }
+      return;
+    }
+    const Real* pc[NG];
+    const Real* pn[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const int c = cur[k], n = nxt[k];
+      pc[k] = is_local(c) ? xi + (unsigned)c : peer_row(reinterpret_cast<const Real*>(p.peer_x[c / p.span]), c / p.span, si) + c;
+      pn[k] = is_local(n) ? xn + (unsigned)n : peer_row(reinterpret_cast<const Real*>(p.peer_x[n / p.span]), n / p.span, sn) + n;
+    }
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      xc[k] = ld_sys(pc[k]);
+      xnext[k] = ld_sys(pn[k]);
+    }
+  }
+
+  // mirrors a freshly written child (state, ancestor) into the halos of the owner's neighbour ranks
+  __device__ __forceinline__ void st_halo(int owner, int n, Real x, int anc) const {
+    const int o = n - owner * p.span;
+    if (o < p.halo && owner > 0) {
+      peer_row(reinterpret_cast<Real*>(p.peer_x[owner - 1]), owner - 1, sx)[n] = x;
+      peer_row(p.peer_anc[owner - 1], owner - 1, sa)[n] = anc;
+    }
+    if (o >= p.span - p.halo && owner + 1 < p.R) {
+      peer_row(reinterpret_cast<Real*>(p.peer_x[owner + 1]), owner + 1, sx)[n] = x;
+      peer_row(p.peer_anc[owner + 1], owner + 1, sa)[n] = anc;
+    }
   }
 
   // Hides how a row pointer was derived, so that row[index] compiles to ONE IMAD.WIDE.U32 on a
@@ -441,6 +526,7 @@ struct PfKernel {
 
   // lineages [c0, c0 + len) of generation tau (ancestor-ring slot `slot_a`) walked back `nlev`
   // generations to smoothing time i (state-ring slot `si`); len <= kChase * kSmootherThreads
+  template <bool DIST>
   __device__ void smooth_round(const Real* lw, double m_tau, const Real* xr, const int* ar, double y,
                                int nlev, int slot_a, int si, int c0, int len,
                                double (&acc)[kMaxParams + 1]) {
@@ -477,18 +563,14 @@ struct PfKernel {
     } else {
       for (int lvl = 1; lvl < nlev; ++lvl) {
         const int* a = opaque(ar + (size_t)slot * NS);
-#pragma unroll
-        for (int k = 0; k < kChase; ++k)
-          if (k < kmax) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
+        hop<DIST>(cur, kmax, a, slot, keep);
         slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
       if (nlev > 0) {
         const int* a = opaque(ar + (size_t)slot * NS);
 #pragma unroll
-        for (int k = 0; k < kChase; ++k) {
-          nxt[k] = cur[k];
-          if (k < kmax) cur[k] = ld_ring<int>(a, p.peer_anc, slot, cur[k], keep);
-        }
+        for (int k = 0; k < kChase; ++k) nxt[k] = cur[k];
+        hop<DIST>(cur, kmax, a, slot, keep);
       }
     }
     const int sn = (si + 1 == p.RX) ? 0 : si + 1;
@@ -505,9 +587,8 @@ struct PfKernel {
         const int kk = h * kHalf + k;
         const int jl = kk * ST + st;
         l[k] = (jl < len) ? ld_hint(lw + (unsigned)(c0 + jl), once) : (Real)(-INFINITY);
-        xc[k] = ld_ring<Real>(xi, reinterpret_cast<Real* const*>(p.peer_x), si, cur[kk], once);
-        xnext[k] = ld_ring<Real>(xn, reinterpret_cast<Real* const*>(p.peer_x), sn, nxt[kk], once);
       }
+      gather_states<DIST, kHalf>(xi, xn, si, sn, cur + h * kHalf, nxt + h * kHalf, xc, xnext, once);
 #pragma unroll
       for (int k = 0; k < kHalf; ++k) {
         const int jl = (h * kHalf + k) * ST + st;
@@ -544,7 +625,8 @@ struct PfKernel {
     double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
     constexpr int kRound = kChase * kSmootherThreads;
     for (int c0 = j_begin; c0 < j_end; c0 += kRound)
-      smooth_round(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
+      if (GENERAL && dist) smooth_round<true>(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
+      else smooth_round<false>(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
 #pragma unroll
     for (int k = 0; k <= kMaxParams; ++k) acc[k] = warp_sum(acc[k]);
     if (lane == 0) {
@@ -570,9 +652,9 @@ struct PfKernel {
     const int N = p.N, T = p.T, L = p.L;
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
-    const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS - lo;
-    const Real* lwr = reinterpret_cast<const Real*>(p.logw) + (size_t)ws * p.RW * NS - lo;
-    const int* ar = p.anc_ring + (size_t)ws * p.RA * NS - lo;
+    const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
+    const Real* lwr = reinterpret_cast<const Real*>(p.logw) + (size_t)ws * p.RW * NS + p.halo - lo;
+    const int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const int j_begin = min(g * p.per_cta, N);
     const int j_end = min(j_begin + p.per_cta, N);
@@ -677,7 +759,7 @@ struct PfKernel {
   __device__ void children_chunk(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
                                  int* anc_new, const double* inj_z_t, const double* inj_u_t, int t,
                                  double u, unsigned long long eval_id, double y_prop, double y_obs,
-                                 int c0, int len, int n_lo, int n_hi, bool remote, double& mx) {
+                                 int c0, int len, int n_lo, int n_hi, bool remote, int owner, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
     int top = 1;
     while (top * 2 <= len) top *= 2;
@@ -759,9 +841,10 @@ struct PfKernel {
           if (p.anc_smem) *reinterpret_cast<ushort2*>(anc_sh + n) = make_ushort2((unsigned short)(c0 + j[2 * h]), (unsigned short)(c0 + j[2 * h + 1]));
           else if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(c0 + j[2 * h], c0 + j[2 * h + 1]);
           else st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
+          if (dist) { st_halo(owner, n, xa, c0 + j[2 * h]); st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         } else {
-          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); }
-          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); }
+          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); if (dist) st_halo(owner, n, xa, c0 + j[2 * h]); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); if (dist) st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         }
         PFB_TICK(15);
       }
@@ -776,7 +859,7 @@ struct PfKernel {
                                int c0, int len, int n_lo, int n_hi, double& mx) {
     if (!dist) {
       children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
-                     y_obs, c0, len, n_lo, n_hi, false, mx);
+                     y_obs, c0, len, n_lo, n_hi, false, 0, mx);
       return;
     }
     if (n_hi <= n_lo) return;
@@ -785,13 +868,13 @@ struct PfKernel {
       const int s_lo = max(n_lo, r * p.span), s_hi = min(n_hi, (r + 1) * p.span);
       if (r == p.rank) {
         children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
-                       y_obs, c0, len, s_lo, s_hi, false, mx);
+                       y_obs, c0, len, s_lo, s_hi, false, r, mx);
       } else {  // global-index views of rank r's generation-t rows
-        Real* xv = reinterpret_cast<Real*>(p.peer_x[r]) + (size_t)sx * NS - (size_t)r * p.span;
-        Real* lv = reinterpret_cast<Real*>(p.peer_lw[r]) + (size_t)sw * NS - (size_t)r * p.span;
-        int* av = p.peer_anc[r] + (size_t)sa * NS - (size_t)r * p.span;
+        Real* xv = peer_row(reinterpret_cast<Real*>(p.peer_x[r]), r, sx);
+        Real* lv = peer_row(reinterpret_cast<Real*>(p.peer_lw[r]), r, sw);
+        int* av = peer_row(p.peer_anc[r], r, sa);
         children_chunk(tile, x_prev, xv, lv, av, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs, c0,
-                       len, s_lo, s_hi, true, mx);
+                       len, s_lo, s_hi, true, r, mx);
       }
     }
   }
@@ -811,9 +894,9 @@ struct PfKernel {
     const size_t NS = (size_t)p.NS;
     // ring rows are addressed with GLOBAL particle indices: the views are shifted by the first index
     // this rank holds (0 on a single GPU)
-    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS - lo;
-    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS - lo;
-    int* ar = p.anc_ring + (size_t)ws * p.RA * NS - lo;
+    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
+    Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS + p.halo - lo;
+    int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const unsigned long long eval_id = p.eval_ids[b];
     const size_t ib = p.inject_per_filter ? (size_t)b : 0;
@@ -835,6 +918,7 @@ struct PfKernel {
 
     // ---- generation 0 (standard.py:62-67): stationary draw or fixed value, uniform weights (fully
     //      adapted filter: look-ahead weights p(y_1 | x_0))
+    sx = sw = sa = 0;  // generation 0 lives in slot 0 of every ring
     double mx0 = -INFINITY;
     for (int pp = (j_begin >> 1) + tid; pp < ((j_end + 1) >> 1); pp += BLOCK) {
       Real z[2] = {0, 0};
@@ -847,6 +931,7 @@ struct PfKernel {
           const Real x0 = p.gen_init ? Ops::init(sh_c, z[e]) : (Real)p.initial_state;
           const Real l0 = kFA ? Ops::logweight(sh_c, x0, __ldg(obs + 1)) : (Real)0;
           xr[n] = x0;
+          if (dist) st_halo(p.rank, n, x0, 0);
           lwr[n] = l0;
           mx0 = dmax(mx0, (double)l0);
           if (p.ws_per_filter) ar[n] = 0;  // generation-0 ancestors are never followed
@@ -1018,7 +1103,7 @@ struct PfKernel {
         // search all of it (resampling.pyx:33-42: unsorted uniforms, ancestors in any tile)
         exchange(0.0);
         children_chunk(p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
-                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, mx);
+                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, 0, mx);
       }
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);

@@ -440,8 +440,12 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.NS = R > 1 ? G_loc * per : (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
+  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
   p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0; p.sjobs0 = 0;
+  // distributed filter: ring rows are [halo | own span | halo] (mirrors of both neighbours' nearest
+  // states and ancestors: lineage walks across a rank boundary stay in local memory)
+  p.halo = R > 1 ? (p.span < (1 << 17) ? p.span : (1 << 17)) : 0;
+  if (R > 1) p.NS = p.span + 2 * p.halo;
   p.RX = history ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
   p.RA = history ? T + 1 : L + 2;
   p.RW = history ? T + 1 : 3;

@@ -18,6 +18,8 @@ ap.add_argument("--T", type=int, default=50)
 ap.add_argument("--L", type=int, default=10)
 ap.add_argument("--dtype", default="float64")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--no-smoother", action="store_true")
+ap.add_argument("--general", action="store_true", help="single GPU: general kernel flavour (stratified resampling)")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -29,12 +31,13 @@ for k in a.log2:
     N = 1 << k
     if world > 1:
         dpf = DistributedParticleFilter("lgss", a.dtype, local)
-        dpf.prepare(obs, bench.THETA_LGSS, N, a.L, seed=1)
+        dpf.prepare(obs, bench.THETA_LGSS, N, a.L, not a.no_smoother, seed=1)
         eng = dpf.engine
     else:
         from qnmh_sysid2018_b200.engine import Engine
         eng = Engine("lgss", a.dtype, local)
-        eng.configure(obs, bench.THETA_LGSS, N, a.L, True, True, 0.0, "systematic", seed=1)
+        eng.configure(obs, bench.THETA_LGSS, N, a.L, not a.no_smoother, True, 0.0,
+                      "stratified" if a.general else "systematic", seed=1)
     ms = []
     for _ in range(a.reps):
         if world > 1:
