@@ -996,13 +996,13 @@ struct PfKernel {
         A += chunk_total;
       }
       PFB_TICK(0);
-      {
+      exchange_arrive(A);
+      PFB_TICK(9);
+      {  // the filtered-mean partial is not on the path to the exchange: reduce it behind the arrival
         const double f = block_sum1(accF);
         if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * p.G_loc + g_loc] = f;
       }
       PFB_TICK(1);
-      exchange_arrive(A);
-      PFB_TICK(9);
       exchange_wait(s_target);
       PFB_TICK(2);
       // prefix over the group + this CTA's children range, evaluated by every warp on its own
