@@ -229,6 +229,7 @@ __device__ __forceinline__ void load_step_consts(uint32_t c_addr, double (&c)[kN
   if (MODEL == kModelLGSS) {
     c[C_SIGE_OR_RHO] = lds_f64(c_addr + 8 * C_SIGE_OR_RHO);
     c[C_LOGSIGE] = lds_f64(c_addr + 8 * C_LOGSIGE);
+    c[C_FA_A] = lds_f64(c_addr + 8 * C_FA_A);  // LGSS: 1 / sigma_e
   }
   if (MODEL == kModelLGSSFA) {
     c[C_STDEV] = lds_f64(c_addr + 8 * C_STDEV);
@@ -262,7 +263,9 @@ struct ModelOps<MODEL, double> {
   // evaluate_obs = scipy.stats.norm.logpdf
   static __device__ __forceinline__ double logweight(const double* c, double x, double y) {
     if (MODEL == kModelLGSS) {
-      const double zz = __ddiv_rn(__dsub_rn(y, x), c[C_SIGE_OR_RHO]);
+      // (y - x) * (1 / sigma_e): one rounding more than the reference's division (<= 1 ulp on the
+      // log-weight; particles are untouched), 12 instructions less on the filter warps' critical path
+      const double zz = __dmul_rn(__dsub_rn(y, x), c[C_FA_A]);
       return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), c[C_LOGSIGE]);
     } else if (MODEL == kModelLGSSFA) {  // log p(y_next | x) = N(y; mu + phi (x - mu), sv^2 + se^2)
       const double pred = __dadd_rn(c[C_MU], __dmul_rn(c[C_PHI], __dsub_rn(x, c[C_MU])));

@@ -449,9 +449,15 @@ struct PfKernel {
       for (int k = 0; k < kChase; ++k) far |= !is_local(cur[k]);
     }
     if (!DIST || !far) {
+      // live items are guarded per gather group (one uniform branch per 7 loads; a per-item predicate
+      // costs two instructions per hop and lineage); idle items of a live group re-walk lineage c0
 #pragma unroll
-      for (int k = 0; k < kChase; ++k)
-        if (k < kmax) cur[k] = ld_hint(a + (unsigned)cur[k], keep);
+      for (int g = 0; g < kChase / kGather; ++g) {
+        if (g * kGather < kmax) {
+#pragma unroll
+          for (int k = g * kGather; k < (g + 1) * kGather; ++k) cur[k] = ld_hint(a + (unsigned)cur[k], keep);
+        }
+      }
       return;
     }
     const int* ptr[kChase];
@@ -548,16 +554,24 @@ struct PfKernel {
       for (int lvl = 1; lvl < nlev; ++lvl) {
         const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
-        for (int k = 0; k < kChase; ++k)
-          if (k < kmax) cur[k] = row[cur[k]];
+        for (int g = 0; g < kChase / kGather; ++g) {
+          if (g * kGather < kmax) {
+#pragma unroll
+            for (int k = g * kGather; k < (g + 1) * kGather; ++k) cur[k] = row[cur[k]];
+          }
+        }
         slot = (slot == 0) ? p.RA - 1 : slot - 1;
       }
       if (nlev > 0) {
         const unsigned short* row = sh_anc + slot * p.anc_stride;
 #pragma unroll
-        for (int k = 0; k < kChase; ++k) {
-          nxt[k] = cur[k];
-          if (k < kmax) cur[k] = row[cur[k]];
+        for (int k = 0; k < kChase; ++k) nxt[k] = cur[k];
+#pragma unroll
+        for (int g = 0; g < kChase / kGather; ++g) {
+          if (g * kGather < kmax) {
+#pragma unroll
+            for (int k = g * kGather; k < (g + 1) * kGather; ++k) cur[k] = row[cur[k]];
+          }
         }
       }
     } else {

@@ -111,6 +111,7 @@ void host_consts(int model, const double* th, double* c) {
     c[C_SIGE_OR_RHO] = se;
     c[C_LOGSIGE] = std::log(se);
     c[C_R] = std::pow(se, -2.0);
+    if (model == kModelLGSS) c[C_FA_A] = 1.0 / se;  // reciprocal used by the device log-weight
     if (model == kModelLGSSFA) {
       const double tot = sv * sv + se * se;
       c[C_STDEV] = std::sqrt(sv * sv * se * se / tot);
