@@ -88,6 +88,8 @@ struct DeviceProblem {
   double* filt_part;  // [B][T+1][G]
   double* smo_part;   // [B][T+1][G][P+1]
   int* traj_k;        // [B]
+  void* s_ring;       // [n_ws][3][NS] shifted weights exp(logw - m) of the last generations: written by
+                      // phase A, re-read by the smoother warps (no second exp)
   double* cdf_g;      // [n_ws][NS] normalised CDF in global memory (multinomial resampling only)
   int* traj_idx;      // [B]
   long long* prof;    // [grid][kProfSlots] per-phase cycle counters (PFB_PROFILE builds only)
@@ -370,7 +372,7 @@ struct PfKernel {
 
   // ---- tile load: tile[jl] = exp(logw[j] - m) for the sub-chunk [c0, c0+len); optional sum s*x
   __device__ void load_chunk(double* tile, const Real* lw, const Real* xg, int c0, int len, double m,
-                             double* accF) {
+                             double* accF, Real* s_out) {
     Real l[ITEMS], xv[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -385,6 +387,7 @@ struct PfKernel {
       const double s = (jl < len) ? shifted_weight<Real>(l[k], m) : 0.0;
       if (accF) f += (kFA ? ((jl < len) ? 1.0 : 0.0) : s) * (double)xv[k];
       tile[jl] = s;
+      if (s_out && jl < len) s_out[c0 + jl] = (Real)s;
     }
     if (accF) *accF += f;
     fsync();
@@ -600,14 +603,14 @@ struct PfKernel {
       for (int k = 0; k < kHalf; ++k) {
         const int kk = h * kHalf + k;
         const int jl = kk * ST + st;
-        l[k] = (jl < len) ? ld_hint(lw + (unsigned)(c0 + jl), once) : (Real)(-INFINITY);
+        l[k] = (jl < len) ? ld_hint(lw + (unsigned)(c0 + jl), once) : (Real)0;  // stored shifted weight
       }
       gather_states<DIST, kHalf>(xi, xn, si, sn, cur + h * kHalf, nxt + h * kHalf, xc, xnext, once);
 #pragma unroll
       for (int k = 0; k < kHalf; ++k) {
         const int jl = (h * kHalf + k) * ST + st;
         const Real xck = xc[k], xnk = xnext[k];
-        const double sw = (jl < len) ? shifted_weight<Real>(l[k], m_tau) : 0.0;
+        const double sw = (double)l[k];
         double gr[kMaxParams];
         Ops::gradient(sh_c, xnk, xck, y, gr);
         const double t0 = (double)xck * sw;
@@ -633,7 +636,7 @@ struct PfKernel {
                               const double* obs, int tau, int i, int j_begin, int j_end) {
     const int st = tid - BLOCK;
     const int swarp = st >> 5;
-    const Real* lw = lwr + (size_t)(tau % p.RW) * p.NS;
+    const Real* lw = lwr + (size_t)(tau % 3) * p.NS;  // row of the shifted-weight ring
     const int slot_a = tau % p.RA, si = i % p.RX;
     const double y = __ldg(obs + i);
     double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -667,7 +670,7 @@ struct PfKernel {
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
     const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
-    const Real* lwr = reinterpret_cast<const Real*>(p.logw) + (size_t)ws * p.RW * NS + p.halo - lo;
+    const Real* lwr = reinterpret_cast<const Real*>(p.s_ring) + (size_t)ws * 3 * NS + p.halo - lo;  // shifted weights
     const int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const int j_begin = min(g * p.per_cta, N);
@@ -958,13 +961,13 @@ struct PfKernel {
     // smoother bookkeeping: generation tau <-> sequence number seq0 + tau; jobs of this evaluation
     const unsigned seq0 = (unsigned)b_idx * (unsigned)(T + 2) + 1u;
     const int n_reg_jobs = (p.do_smoother && T > L) ? T - L : 0;  // lag times L .. T-1
-    publish_generation(seq0, 0, m);
 
     for (int t = 1; t <= T + 1; ++t) {
       if (aborted) return;
       const int tau = t - 1;
       const Real* x_prev = xr + (size_t)sx * NS;  // generation tau: the slots written last step
       const Real* lw_prev = lwr + (size_t)sw * NS;
+      Real* s_row = p.do_smoother ? reinterpret_cast<Real*>(p.s_ring) + ((size_t)ws * 3 + (size_t)(tau % 3)) * NS + p.halo - lo : nullptr;
       sx = (sx + 1 == p.RX) ? 0 : sx + 1;
       sw = (sw + 1 == p.RW) ? 0 : sw + 1;
       sa = (sa + 1 == p.RA) ? 0 : sa + 1;
@@ -1003,7 +1006,7 @@ struct PfKernel {
         const int c0 = j_begin + c * kChunk;
         const int len = min(kChunk, j_end - c0);
         double* tile = sh_s + (resident ? c * kChunk : 0);
-        load_chunk(tile, lw_prev, x_prev, c0, len, m, &accF);
+        load_chunk(tile, lw_prev, x_prev, c0, len, m, &accF, s_row);
         PFB_TICK(8);
         chunk_total = scan_chunk(tile);
         if (resident && tid == 0) sh_red[264 + c] = chunk_total;  // sub-chunk totals for phase B
@@ -1011,6 +1014,9 @@ struct PfKernel {
       }
       PFB_TICK(0);
       exchange_arrive(A);
+      // generation tau is complete everywhere (exchange 2 of the previous step) and this CTA's part of
+      // its shifted weights is stored: the smoother warps may start the job of lag time tau
+      publish_generation(seq0 + (unsigned)tau, tau, m);
       PFB_TICK(9);
       {  // the filtered-mean partial is not on the path to the exchange: reduce it behind the arrival
         const double f = block_sum1(accF);
@@ -1077,7 +1083,7 @@ struct PfKernel {
           const int c0 = j_begin + c * kChunk;
           const int len = min(kChunk, j_end - c0);
           fsync();
-          load_chunk(sh_s, lw_prev, x_prev, c0, len, m, nullptr);
+          load_chunk(sh_s, lw_prev, x_prev, c0, len, m, nullptr, nullptr);
           chunk_total = scan_chunk(sh_s);
 #pragma unroll
           for (int k = 0; k < ITEMS; ++k) {
@@ -1144,7 +1150,6 @@ struct PfKernel {
         exchange_wait();
         PFB_TICK(6);
         m = xchg_max();
-        publish_generation(seq0 + (unsigned)t, t, m);
         PFB_TICK(7);
       }
     }

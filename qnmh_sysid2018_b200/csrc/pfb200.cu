@@ -172,7 +172,7 @@ struct pfb200_handle {
   int n_ws = 0;
   // device buffers
   DevBuf obs, consts, evals, inj_z0, inj_u, inj_z, inj_uf;
-  DevBuf x_ring, logw, anc, cdf_g, xval, xcount, abortf;
+  DevBuf x_ring, logw, anc, s_ring, cdf_g, xval, xcount, abortf;
   DevBuf stat_m, stat_S, filt_part, smo_part, traj_k, traj_idx;
   DevBuf ll_terms, log_like, filt, smo, grad, traj, scratch, prof;
   std::vector<double> h_consts;
@@ -255,7 +255,7 @@ int pfb200_destroy(pfb200_handle* h) {
   cudaStreamSynchronize(h->stream);
   dist_close(h);
   DevBuf* bufs[] = {&h->obs, &h->consts, &h->evals, &h->inj_z0, &h->inj_u, &h->inj_z, &h->inj_uf, &h->x_ring,
-                    &h->logw, &h->anc, &h->xval, &h->xcount, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
+                    &h->logw, &h->anc, &h->s_ring, &h->cdf_g, &h->xval, &h->xcount, &h->abortf, &h->stat_m, &h->stat_S, &h->filt_part,
                     &h->smo_part, &h->traj_k, &h->traj_idx, &h->ll_terms, &h->log_like, &h->filt, &h->smo,
                     &h->grad, &h->traj, &h->scratch, &h->prof};
   for (DevBuf* b : bufs) b->release();
@@ -484,6 +484,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * p.NS * real_sz));
   CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
   CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
+  if (do_smoother) CUDA_TRY(h->s_ring.reserve((size_t)h->n_ws * 3 * p.NS * real_sz));
   if (resampling == PFB200_RESAMPLE_MULTINOMIAL) CUDA_TRY(h->cdf_g.reserve((size_t)h->n_ws * p.NS * 8));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
   CUDA_TRY(h->xcount.reserve((size_t)n_groups * 32 * 4));
@@ -521,6 +522,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.smo_part = h->smo_part.as<double>();
   p.traj_k = h->traj_k.as<int>();
   p.cdf_g = h->cdf_g.as<double>();
+  p.s_ring = h->s_ring.ptr;
   p.traj_idx = h->traj_idx.as<int>();
   p.prof = h->prof.as<long long>();
   for (int r = 0; r < 8; ++r) { p.peer_x[r] = p.x_ring; p.peer_lw[r] = p.logw; p.peer_anc[r] = p.anc_ring; p.peer_xval[r] = p.xval; p.peer_xcount[r] = p.xcount; }

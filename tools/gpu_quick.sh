@@ -7,3 +7,5 @@ timeout 120 python tools/run_once.py --T 200 --N 2000 2>&1 | tail -1
 timeout 120 python tools/run_once.py --T 200 --N 500 2>&1 | tail -1
 timeout 120 python tools/run_once.py --T 200 --N 65536 --model sv 2>&1 | tail -1
 timeout 120 python tools/run_once.py --T 50 --N 16777216 2>&1 | tail -1
+timeout 120 python tools/run_once.py --T 200 --L 1 2>&1 | tail -1
+timeout 120 python tools/run_once.py --T 200 --L 5 2>&1 | tail -1
