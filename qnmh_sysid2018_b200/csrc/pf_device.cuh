@@ -63,6 +63,16 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t e
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
+// Same function with the ten round keys precomputed on the host (kernel parameters live in the
+// constant bank, so a key is an operand of the round's XOR instead of two additions per round).
+__device__ __forceinline__ void philox4x32_10_keys(const unsigned* keys, uint64_t eval_id, unsigned stream,
+                                                   uint32_t t, uint32_t index, uint32_t (&out)[4]) {
+  uint32_t c[4] = {index, t, (uint32_t)eval_id, (uint32_t)(eval_id >> 32) ^ (stream << 28)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c, keys[2 * r], keys[2 * r + 1]);
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
 // uniform in [0,1) with 53 random bits (numpy's uniform() is also [0,1))
 __host__ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
   const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
@@ -162,11 +172,25 @@ __device__ __forceinline__ void sincospi_0_2(double a, double& sn, double& cs) {
   cs = (((k + 1) & 2) != 0) ? -c0 : c0;
 }
 
+__device__ __forceinline__ void normal_pair_from_bits(const uint32_t (&r)[4], double& z_even, double& z_odd);
+__device__ __forceinline__ void normal_pair_from_bits(const uint32_t (&r)[4], float& z_even, float& z_odd);
+// hot-path variant: round keys from the kernel parameters
+template <typename Real>
+__device__ __forceinline__ void philox_normal_pair_keys(const unsigned* keys, uint64_t eval_id, uint32_t t,
+                                                        uint32_t pair, Real& z_even, Real& z_odd) {
+  uint32_t r[4];
+  philox4x32_10_keys(keys, eval_id, kStreamZ, t, pair, r);
+  normal_pair_from_bits(r, z_even, z_odd);
+}
+
 template <>
 __device__ __forceinline__ void philox_normal_pair<double>(uint64_t seed, uint64_t eval_id, uint32_t t,
                                                            uint32_t pair, double& z_even, double& z_odd) {
   uint32_t r[4];
   philox4x32_10(seed, eval_id, kStreamZ, t, pair, r);
+  normal_pair_from_bits(r, z_even, z_odd);
+}
+__device__ __forceinline__ void normal_pair_from_bits(const uint32_t (&r)[4], double& z_even, double& z_odd) {
   const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
   const double u2 = u01_53(r[2], r[3]);
   const double rad = sqrt_nonneg(-2.0 * log_unit_interval(u1));
@@ -181,6 +205,9 @@ __device__ __forceinline__ void philox_normal_pair<float>(uint64_t seed, uint64_
                                                           uint32_t pair, float& z_even, float& z_odd) {
   uint32_t r[4];
   philox4x32_10(seed, eval_id, kStreamZ, t, pair, r);
+  normal_pair_from_bits(r, z_even, z_odd);
+}
+__device__ __forceinline__ void normal_pair_from_bits(const uint32_t (&r)[4], float& z_even, float& z_odd) {
   const float u1 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
   const float u2 = (float)(r[2] >> 8) * (1.0f / 16777216.0f);
   const float rad = sqrtf(-2.0f * __logf(u1));

@@ -65,6 +65,7 @@ struct DeviceProblem {
   int halo;           // distributed filter: every ring row is [halo | own span | halo]: a rank mirrors the
                       // `halo` nearest states and ancestors of both neighbours, so that lineage walks
                       // across a rank boundary stay in local memory (row stride NS = span + 2 * halo)
+  unsigned pkeys[20]; // Philox round keys of `seed` (key_r = seed + r * Weyl constants)
   unsigned sjobs0;    // smoother jobs completed per CTA before this launch (distributed filter: the peer
                       // counters keep counting across launches; 0 otherwise)
   unsigned long long pol_keep, pol_once;  // L2 cache policies (evict_last / evict_first), created once per handle
@@ -786,9 +787,19 @@ struct PfKernel {
     double cst[kNumConsts];
     load_step_consts<MODEL>(smem_base(sh_c), cst);
     const Real* xp_row = opaque(x_prev + c0);
-    for (int qq = q0 + tid; qq < q1; qq += BLOCK) {
+    // Two lane mappings.  "Shuffle": a warp takes 31 consecutive quads per pass (lanes 0..30) and
+    // lane 31 only searches the first child of the NEXT quad, so that every quad gets the upper end
+    // of its search window from its right neighbour by one shuffle.  "Pair": 32 quads per warp, every
+    // lane runs a second descent for the next quad's first child.  The shuffle mapping executes half
+    // the probes; the pair mapping is compiled into the ITEMS = 9 flavour, whose typical range of
+    // 4096 particles is exactly two passes of 512 quads (it would be three passes of 496).
+    constexpr bool shuffle_map = (ITEMS != PFB_ITEMS_ALT);
+    constexpr int kQuadsPerWarp = shuffle_map ? 31 : 32;
+    for (int qb = q0 + warp * kQuadsPerWarp; qb < q1; qb += kWarps * kQuadsPerWarp) {  // warp-uniform
+      const int qq = qb + lane;
+      const bool own = lane < kQuadsPerWarp && qq < q1;
       const int nb = 4 * qq;
-      const bool full = nb >= n_lo && nb + 3 < n_hi;
+      const bool full = own && nb >= n_lo && nb + 3 < n_hi;
       int j[4];
       if (GENERAL && p.resampling == 2) {
         // multinomial: j = #{ k < N-1 : cdf[k] < u_n } (searchsorted side='left' with the last CDF
@@ -809,22 +820,29 @@ struct PfKernel {
           }
         }
       } else {
-        // first child of this quad and of the next one side by side, then the inner three children
-        // inside the window the two answers span (never a second full descent)
-        const double pa = position(nb, u, t, inj_u_t, eval_id);
-        const double pb = (nb + 4 < p.N) ? position(nb + 4, u, t, inj_u_t, eval_id) : INFINITY;
+        // one descent for the first child of the quad; the first child of the next quad (lane + 1)
+        // closes the window in which the three inner children are searched (never a second full
+        // descent)
+        const double pa = (nb < p.N) ? position(nb, u, t, inj_u_t, eval_id) : INFINITY;
         double pin[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e)
           pin[e] = (nb + 1 + e < p.N) ? position(nb + 1 + e, u, t, inj_u_t, eval_id) : INFINITY;
         int la, lb, li[3];
-        upper_bound_pair(ta, pa, pb, len, top, la, lb);
+        if (shuffle_map) {
+          la = upper_bound_tile(ta, pa, len, top);
+          lb = __shfl_down_sync(0xffffffffu, la, 1);  // lane 31 keeps its own value: empty window
+        } else {
+          const double pb = (nb + 4 < p.N) ? position(nb + 4, u, t, inj_u_t, eval_id) : INFINITY;
+          upper_bound_pair(ta, pa, pb, len, top, la, lb);
+        }
         upper_bound_window3(ta, pin, la, lb, li);
         j[0] = min(la, len - 1);
 #pragma unroll
         for (int e = 0; e < 3; ++e) j[1 + e] = min(li[e], len - 1);
       }
       PFB_TICK(11);
+      if (!own) continue;
       Real xp[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) xp[e] = ld_cg(xp_row + (unsigned)j[e]);
@@ -836,7 +854,7 @@ struct PfKernel {
           z0 = (n >= n_lo && n < n_hi) ? (Real)ld_cg(inj_z_t + n) : (Real)0;
           z1 = (n + 1 >= n_lo && n + 1 < n_hi) ? (Real)ld_cg(inj_z_t + n + 1) : (Real)0;
         } else {
-          philox_normal_pair<Real>(p.seed, eval_id, (uint32_t)t, (uint32_t)(2 * qq + h), z0, z1);
+          philox_normal_pair_keys<Real>(p.pkeys, eval_id, (uint32_t)t, (uint32_t)(2 * qq + h), z0, z1);
         }
 #ifdef PFB_PROFILE
         if (z0 == (Real)123456.789) mx = 0.0;

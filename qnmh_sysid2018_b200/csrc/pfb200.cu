@@ -316,6 +316,15 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   return PFB200_OK;
 }
 
+// seed + its Philox4x32 key schedule: key_r = key_0 + r * (0x9E3779B9, 0xBB67AE85)
+static void set_seed(DeviceProblem& p, uint64_t seed) {
+  p.seed = seed;
+  for (int r = 0; r < 10; ++r) {
+    p.pkeys[2 * r] = (unsigned)seed + (unsigned)r * 0x9E3779B9u;
+    p.pkeys[2 * r + 1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u;
+  }
+}
+
 static int upload_params(pfb200_handle* h, const double* theta, uint64_t seed, const uint64_t* eval_ids) {
   const int B = h->prob.B;
   h->h_consts.resize((size_t)B * kNumConsts);
@@ -324,7 +333,7 @@ static int upload_params(pfb200_handle* h, const double* theta, uint64_t seed, c
     host_consts(h->model, theta + (size_t)b * h->P, h->h_consts.data() + (size_t)b * kNumConsts);
     h->h_evals[b] = eval_ids ? eval_ids[b] : (unsigned long long)b;
   }
-  h->prob.seed = seed;
+  set_seed(h->prob, seed);
   CUDA_TRY(cudaMemcpyAsync(h->consts.ptr, h->h_consts.data(), h->h_consts.size() * sizeof(double),
                            cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->evals.ptr, h->h_evals.data(), h->h_evals.size() * sizeof(unsigned long long),
@@ -461,7 +470,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.anc_smem = anc_smem ? 1 : 0;
   p.anc_stride = anc_stride;
   p.initial_state = initial_state;
-  p.seed = seed;
+  set_seed(p, seed);
   p.spin_limit = h->opt_spin_limit;
   p.pol_keep = h->pol_keep;
   p.pol_once = h->pol_once;
