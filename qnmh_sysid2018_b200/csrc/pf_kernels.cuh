@@ -2,23 +2,28 @@
 //
 // One launch runs the whole time loop t = 1..T of one or many filters.  A filter is worked on by a
 // GROUP of G cooperating CTAs (G = 1 for the batched small-N case, G = all resident CTAs for one
-// large filter); a group loops over the filters assigned to it.  Per time step a CTA
+// large filter); a group loops over the filters assigned to it.  A CTA is warp-specialised: BLOCK
+// filter threads run the time-critical loop, one warpgroup of smoother threads follows up to two
+// time steps behind (the register file is re-split between the two roles with setmaxnreg).
 //
+// Filter warps, per time step:
 //   phase A (generation tau = t-1, parents j in the CTA's contiguous range)
 //     s[j]   = exp(logw[j] - m_tau)                       weight normalisation, standard.py:90-93
+//              (also stored in a 3-deep ring for the smoother warps)
 //     tile-local inclusive scan of s  -> CDF tile in shared memory         resampling.pyx:75
 //     partial sums  sum s*x  (filtered mean, standard.py:101)
-//     fixed-lag smoother increment for time i = tau - L: chase L ancestor links through the
-//     ancestor ring, accumulate s * (x_i, d log p / d theta)                standard.py:146-169
 //   exchange 1: every CTA publishes its tile total; all CTAs form the same exclusive prefix
 //   phase B (generation t, children n whose position (n+u)/N falls into the CTA's CDF range --
 //            contiguous because systematic resampling is monotone)
 //     a[n]   = first j with (n+u)/N < c[j]   (search in the shared-memory CDF tile) resampling.pyx:78-83
 //     x_t[n] = f(x_{t-1}[a[n]]) + noise(t, n),  logw_t[n] = log g(y_t | x_t[n])   standard.py:85-88
 //   exchange 2: per-CTA max of the new log-weights -> m_t
+// Smoother warps, per lag time tau = L .. T (standard.py:146-169):
+//     walk the lineages of the CTA's index range L generations back through the ancestor ring,
+//     accumulate s_tau * (x_i, d log p / d theta) for the smoothing time i = tau - L
 //
 // so neither the CDF nor the normalised weights ever touch global memory.  Generations live in
-// time-major rings: x (L+3 deep), ancestors (L+2), log-weights (3).
+// time-major rings: x (L+3 deep), ancestors (L+2), log-weights (3), shifted weights (3).
 //
 // The CDF tile of a CTA stays resident in shared memory across the two phases when it fits
 // (`tile_cap`); it is scanned in sub-chunks of BLOCK*ITEMS parents.  Larger tiles stream through
@@ -35,13 +40,7 @@ namespace pfb200 {
 #endif
 constexpr int kProfSlots = 16;
 #ifndef PFB_CHASE
-#define PFB_CHASE 21
-#endif
-#ifndef PFB_SMOOTH_BATCH
-#define PFB_SMOOTH_BATCH 0  // lineages per thread in flight in the smoother job (0 = ITEMS)
-#endif
-#ifndef PFB_SMOOTH_SPLIT
-#define PFB_SMOOTH_SPLIT 1  // 1: half of the deferred smoother job per exchange wait; 0: all of it behind exchange 1
+#define PFB_CHASE 21  // lineages a smoother thread walks at once (multiple of 7)
 #endif
 
 struct DeviceProblem {
@@ -125,7 +124,6 @@ struct PfKernel {
   double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
   unsigned short* sh_anc;  // [RA][anc_stride] shared-memory ancestor ring (anc_smem mode)
-  double* sh_m;        // [4] max log-weight of the last generations (filter -> smoother warps)
   double* sh_sred;     // [kSmootherWarps][kMaxParams + 1] smoother reduction scratch
   unsigned* sh_flags;  // [0] sequence number of the last complete generation, [1] smoother jobs done (G == 1)
   const int tid, lane, warp, g_loc, q, g;  // g: CTA index inside the (possibly multi-GPU) group
@@ -142,11 +140,11 @@ struct PfKernel {
   long long prof_t = 0;
 #endif
 
-  __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst, double* shm,
-                      double* sred, unsigned* flags)
+  __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst, double* sred,
+                      unsigned* flags)
       : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst),
         sh_anc(reinterpret_cast<unsigned short*>(smem + prob.tile_cap + (prob.G > 1 ? prob.G : 1))),
-        sh_m(shm), sh_sred(sred), sh_flags(flags), tid(threadIdx.x),
+        sh_sred(sred), sh_flags(flags), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g_loc(blockIdx.x % prob.G_loc),
         q(blockIdx.x / prob.G_loc), g(prob.rank * prob.G_loc + blockIdx.x % prob.G_loc),
         dist(GENERAL && prob.R > 1), lo(prob.rank * prob.span), pow2N((prob.N & (prob.N - 1)) == 0), invN(1.0 / (double)prob.N),
@@ -228,12 +226,10 @@ struct PfKernel {
   }
 
   // ---- filter warps -> smoother warps of the same CTA: generation `seq` is complete everywhere
-  //      (this CTA has passed the group barrier that follows its children) and its max log-weight
-  __device__ void publish_generation(unsigned seq, int tau, double m) {
-    if (tid == 0) {
-      sh_m[tau & 3] = m;
-      st_release_cta_shared_u32(sh_flags, seq);
-    }
+  //      (this CTA has passed the group barrier that follows its children) and this CTA's part of
+  //      its shifted weights is stored
+  __device__ void publish_generation(unsigned seq) {
+    if (tid == 0) st_release_cta_shared_u32(sh_flags, seq);
   }
 
   // ---- smoother warps: wait for a generation / report a finished job
@@ -419,19 +415,10 @@ struct PfKernel {
 
   // ---- fixed-lag smoother (standard.py:146-169), run by the smoother warps of the CTA while the
   //      filter warps go on with the next time steps.  A job takes the weights of generation tau
-  //      (s[j] = exp(logw_tau[j] - m_tau), recomputed from the log-weight ring), walks every lineage
+  //      (s[j] = exp(logw_tau[j] - m_tau), stored by phase A in the shifted-weight ring), walks every lineage
   //      of this CTA's index range back to smoothing time i and accumulates s * (x_i, grad log p).
   //      It only reads generations that are complete; the filter warps wait for it (exchange_wait)
   //      before they overwrite the ring slots it reads.
-  // element n (global index) of ring row `slot`: own memory, or the owner rank's memory over NVLink
-  template <typename T>
-  __device__ __forceinline__ T ld_ring(const T* local_row_view, T* const* peer_base, int slot, int n,
-                                       uint64_t pol) const {
-    if (!dist || (unsigned)(n - lo) < (unsigned)p.span) return ld_hint(local_row_view + (unsigned)n, pol);  // n >= 0: one IMAD.WIDE.U32
-    const int r = n / p.span;
-    return ld_sys(peer_base[r] + (size_t)slot * p.NS + p.halo + (n - r * p.span));
-  }
-
   // DIST: is global particle n held in this rank's memory (own span or a halo mirror)?
   __device__ __forceinline__ bool is_local(int n) const {
     return (unsigned)(n - lo + p.halo) < (unsigned)(p.span + 2 * p.halo);
@@ -537,7 +524,7 @@ struct PfKernel {
   // lineages [c0, c0 + len) of generation tau (ancestor-ring slot `slot_a`) walked back `nlev`
   // generations to smoothing time i (state-ring slot `si`); len <= kChase * kSmootherThreads
   template <bool DIST>
-  __device__ void smooth_round(const Real* lw, double m_tau, const Real* xr, const int* ar, double y,
+  __device__ void smooth_round(const Real* sw_row, const Real* xr, const int* ar, double y,
                                int nlev, int slot_a, int si, int c0, int len,
                                double (&acc)[kMaxParams + 1]) {
     constexpr int ST = kSmootherThreads;
@@ -604,7 +591,7 @@ struct PfKernel {
       for (int k = 0; k < kHalf; ++k) {
         const int kk = h * kHalf + k;
         const int jl = kk * ST + st;
-        l[k] = (jl < len) ? ld_hint(lw + (unsigned)(c0 + jl), once) : (Real)0;  // stored shifted weight
+        l[k] = (jl < len) ? ld_hint(sw_row + (unsigned)(c0 + jl), once) : (Real)0;  // stored shifted weight
       }
       gather_states<DIST, kHalf>(xi, xn, si, sn, cur + h * kHalf, nxt + h * kHalf, xc, xnext, once);
 #pragma unroll
@@ -633,18 +620,18 @@ struct PfKernel {
   }
 
   // one smoothing time: all lineages of this CTA's range, block sum, partial written for finalize
-  __device__ void smooth_time(int b, const Real* lwr, double m_tau, const Real* xr, const int* ar,
+  __device__ void smooth_time(int b, const Real* swr, const Real* xr, const int* ar,
                               const double* obs, int tau, int i, int j_begin, int j_end) {
     const int st = tid - BLOCK;
     const int swarp = st >> 5;
-    const Real* lw = lwr + (size_t)(tau % 3) * p.NS;  // row of the shifted-weight ring
+    const Real* sw_row = swr + (size_t)(tau % 3) * p.NS;  // row of the shifted-weight ring
     const int slot_a = tau % p.RA, si = i % p.RX;
     const double y = __ldg(obs + i);
     double acc[kMaxParams + 1] = {0.0, 0.0, 0.0, 0.0, 0.0};
     constexpr int kRound = kChase * kSmootherThreads;
     for (int c0 = j_begin; c0 < j_end; c0 += kRound)
-      if (GENERAL && dist) smooth_round<true>(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
-      else smooth_round<false>(lw, m_tau, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
+      if (GENERAL && dist) smooth_round<true>(sw_row, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
+      else smooth_round<false>(sw_row, xr, ar, y, tau - i, slot_a, si, c0, min(kRound, j_end - c0), acc);
 #pragma unroll
     for (int k = 0; k <= kMaxParams; ++k) acc[k] = warp_sum(acc[k]);
     if (lane == 0) {
@@ -671,7 +658,7 @@ struct PfKernel {
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
     const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
-    const Real* lwr = reinterpret_cast<const Real*>(p.s_ring) + (size_t)ws * 3 * NS + p.halo - lo;  // shifted weights
+    const Real* swr = reinterpret_cast<const Real*>(p.s_ring) + (size_t)ws * 3 * NS + p.halo - lo;  // shifted weights
     const int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
     const int j_begin = min(g * p.per_cta, N);
@@ -679,13 +666,12 @@ struct PfKernel {
     const unsigned seq0 = (unsigned)b_idx * (unsigned)(T + 2) + 1u;  // generation tau <-> seq0 + tau
     for (int tau = L; tau < T; ++tau) {
       if (smoother_wait_generation(seq0 + (unsigned)tau)) { aborted = true; return; }
-      smooth_time(b, lwr, sh_m[tau & 3], xr, ar, obs, tau, tau - L, j_begin, j_end);
+      smooth_time(b, swr, xr, ar, obs, tau, tau - L, j_begin, j_end);
       smoother_job_done();
     }
     if (smoother_wait_generation(seq0 + (unsigned)T)) { aborted = true; return; }
-    const double m_T = sh_m[T & 3];
     for (int i = T - 1; i >= ((T - L > 0) ? T - L : 0); --i)
-      smooth_time(b, lwr, m_T, xr, ar, obs, T, i, j_begin, j_end);
+      smooth_time(b, swr, xr, ar, obs, T, i, j_begin, j_end);
     smoother_job_done();
   }
 
@@ -1034,7 +1020,7 @@ struct PfKernel {
       exchange_arrive(A);
       // generation tau is complete everywhere (exchange 2 of the previous step) and this CTA's part of
       // its shifted weights is stored: the smoother warps may start the job of lag time tau
-      publish_generation(seq0 + (unsigned)tau, tau, m);
+      publish_generation(seq0 + (unsigned)tau);
       PFB_TICK(9);
       {  // the filtered-mean partial is not on the path to the exchange: reduce it behind the arrival
         const double f = block_sum1(accF);
@@ -1184,7 +1170,6 @@ __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_k
   extern __shared__ double pf_smem[];
   __shared__ double sh_red[9 * 32 + 8];
   __shared__ double sh_c[kNumConsts];
-  __shared__ double sh_m[4];
   __shared__ double sh_sred[(PFB_SMOOTH_THREADS / 32) * (kMaxParams + 1)];
   __shared__ unsigned sh_flags[4];
   if (threadIdx.x == 0) {
@@ -1192,7 +1177,7 @@ __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_k
     sh_flags[1] = prob.sjobs0;
   }
   __syncthreads();
-  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c, sh_m, sh_sred, sh_flags);
+  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c, sh_sred, sh_flags);
   if (threadIdx.x >= BLOCK) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     if (!prob.do_smoother) return;

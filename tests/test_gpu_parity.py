@@ -215,6 +215,34 @@ def test_batched_filters_match_oracle_each():
         assert int(out["traj_index"][b]) == ref["trajectory_index"]
 
 
+def test_batched_filters_with_several_ctas_each():
+    """Batch + groups of several CTAs: a group runs several filters one after the other, so the
+    exchange counters and the smoother-job counters keep counting across evaluations of one launch."""
+    rng = np.random.default_rng(101)
+    B, N, T, L = 5, 9000, 25, 6
+    theta0 = np.array([0.2, 0.5, 1.0, 0.5])
+    obs = _synthetic_obs("lgss", theta0, T, rng)
+    thetas = theta0 + 0.05 * rng.standard_normal((B, 4))
+    draws = [orc.random_draws(rng, N, T) for _ in range(B)]
+    eng = _engine("lgss", ctas_per_filter=3, max_groups=2)
+    out = eng.run(obs, thetas, N, L, True, True, 0.0, "systematic", draws=draws)
+    assert eng.info("ctas_per_filter") == 3 and eng.info("n_groups") == 2
+    for b in range(B):
+        ref = orc.smoother(orc.MODEL_LGSS, thetas[b], obs, N, L, draws[b])
+        assert abs(out["log_like"][b] - ref["log_like"]) <= RTOL * abs(ref["log_like"])
+        np.testing.assert_allclose(out["smo"][b], ref["smo_state_est"].reshape(-1), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(out["grad_terms"][b], ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
+        assert int(out["traj_index"][b]) == ref["trajectory_index"]
+    # production flavour (Philox): the batch equals the same evaluations run one at a time
+    evals = [11, 12, 13, 14, 15]
+    batch = eng.run(obs, thetas, N, L, True, True, 0.0, "systematic", seed=5, eval_ids=evals)
+    single = _engine("lgss", ctas_per_filter=3)
+    for b in range(B):
+        one = single.run(obs, thetas[b], N, L, True, True, 0.0, "systematic", seed=5, eval_ids=[evals[b]])
+        for k in ("log_like", "filt", "smo", "grad_terms", "traj_index"):
+            np.testing.assert_array_equal(batch[k][b], one[k][0])
+
+
 def test_ring_mode_equals_history_mode():
     """The (L+2)-deep rings must give the same numbers as keeping all T+1 generations."""
     rng = np.random.default_rng(17)
