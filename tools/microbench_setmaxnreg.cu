@@ -1,4 +1,5 @@
-// toy: do setmaxnreg.dec/inc work for a 640-thread CTA with launch bounds (640,1)?
+// Micro-test: setmaxnreg.dec/inc for a 640-thread CTA launched with 96 registers per thread
+// (512 threads -> 88, one warpgroup -> 128); prints the launch register count.  nvcc -gencode arch=compute_100a,code=sm_100a
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int N>
