@@ -258,6 +258,7 @@ struct PfKernel {
 
   // max over the exchanged values; every warp reduces all G values itself (no block barrier)
   __device__ double xchg_max() {
+    if (p.G == 1) return dmax(-INFINITY, sh_x[0]);  // one CTA per filter: nothing to reduce
     double m = -INFINITY;
     for (int i = lane; i < p.G; i += 32) m = dmax(m, sh_x[i]);
 #pragma unroll
@@ -271,6 +272,11 @@ struct PfKernel {
   // agree bit for bit on their common boundary: excl(g) := incl(g-1).
   __device__ void xchg_prefix(double& excl, double& incl, double& total) {
     const int G = p.G;
+    if (G == 1) {  // one CTA per filter: the tile total is the only term
+      excl = 0.0;
+      incl = total = 0.0 + sh_x[0];
+      return;
+    }
     const int W = (G + 31) / 32;
     const int b0 = lane * W;
     double run = 0.0;

@@ -341,6 +341,11 @@ def test_filtered_means_and_loglik_against_exact_kalman():
         o32 = _engine("lgss", dtype).run(obs, theta, 1 << 18, 10, True, True, 0.0, "systematic", seed=21)
         assert abs(o32["log_like"][0] - kf["log_like"]) < 0.3  # documented fp32 bound: ~1e-3 relative
         assert np.abs(o32["filt"][0][1:] - kf["filt_state_est"][1:]).max() < 0.02
+        # fp32 smoother (fp32 rings and normals, fp64 accumulation): same estimates up to Monte Carlo
+        # error of two independent N = 2^18 runs
+        assert np.abs(o32["smo"][0] - out["smo"][0]).max() < 0.08
+        s64, s32 = out["grad_terms"][0].sum(axis=-1), o32["grad_terms"][0].sum(axis=-1)
+        assert np.all(np.isfinite(s32)) and np.abs(s32 - s64).max() < 1.5, (s32, s64)
 
 
 def test_philox_loglik_is_consistent_with_kalman():
