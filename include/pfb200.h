@@ -94,6 +94,9 @@ int pfb200_set_stream(pfb200_handle* h, void* cuda_stream);
  *   "ctas_per_filter"  G: CTAs cooperating on one filter (0 = automatic)
  *   "max_groups"       upper bound on concurrently resident filter groups (0 = automatic)
  *   "spin_limit"       abort a launch whose inter-CTA exchange spins longer than this many polls
+ *   "items"            parents per thread and scan sub-chunk: 7, 9 or 2 (0 = automatic)
+ *   "anc_smem"         1 (default): filters of one CTA and N <= 65535 keep the ancestor ring in
+ *                      shared memory; 0: always in global memory
  *   "dist_world", "dist_rank"  shard ONE filter over several GPUs (see pfb200_dist_* below) */
 int pfb200_set_option(pfb200_handle* h, const char* name, long long value);
 int pfb200_get_info(pfb200_handle* h, const char* name, long long* value);
@@ -107,7 +110,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value);
  *   theta      [B][P] model parameters in the reference's order (get_all_params())
  *   seed, eval_ids[B] (NULL -> 0..B-1): Philox4x32-10 stream = (seed, eval_id); a draw depends only
  *              on (seed, eval_id, time step, particle index), never on the launch geometry
- *   inj_z0 [N], inj_u [T+1] ([T+1][N] for stratified), inj_z [T+1][N], inj_u_final [1]:
+ *   inj_z0 [N], inj_u [T+1] ([T+1][N] for stratified / multinomial), inj_z [T+1][N], inj_u_final [1]:
  *              injected randomness replacing Philox (all four or none; NULL = Philox); with
  *              PFB200_FLAG_INJECT_PER_FILTER each carries a leading [B] dimension.  Row t of
  *              inj_u / inj_z is consumed at time step t (row 0 is unused).
@@ -167,8 +170,8 @@ int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, in
  * a CPU checker). */
 int pfb200_philox_normals(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int n,
                           double* z);
-/* The resampling uniform(s) the Philox path uses at time step t (count = 1 systematic, N stratified;
- * t = -1: the trajectory-draw uniform). */
+/* The resampling uniform(s) the Philox path uses at time step t (count = 1 systematic, N stratified /
+ * multinomial; t = -1: the trajectory-draw uniform). */
 int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, int t, int count,
                            double* u);
 
