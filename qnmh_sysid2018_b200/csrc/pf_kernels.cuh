@@ -40,7 +40,7 @@ namespace pfb200 {
 #endif
 constexpr int kProfSlots = 16;
 #ifndef PFB_CHASE
-#define PFB_CHASE 21  // lineages a smoother thread walks at once (multiple of 7)
+#define PFB_CHASE 28  // lineages a smoother thread walks at once (multiple of 7)
 #endif
 
 struct DeviceProblem {
