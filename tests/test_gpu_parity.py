@@ -183,6 +183,20 @@ def test_multinomial_philox_path_replayed_through_oracle():
     np.testing.assert_array_equal(ring["smo"], out["smo"])
 
 
+@pytest.mark.parametrize("kind,theta,resampling", [("sv", [0.5, 0.95, 0.25], "multinomial"),
+                                                   ("sv_leverage", [0.5, 0.95, 0.25, -0.3], "stratified"),
+                                                   ("sv_leverage", [0.5, 0.95, 0.25, -0.3], "multinomial")])
+def test_sv_models_with_other_resamplers_match_oracle(kind, theta, resampling):
+    """The stochastic-volatility models through the general kernel flavour's other resamplers."""
+    rng = np.random.default_rng(len(resampling) + len(theta))
+    theta = np.array(theta)
+    obs = _synthetic_obs(kind, theta, 30, rng)
+    for N, G in ((900, 1), (7000, 3)):
+        draws = orc.random_draws(rng, N, 30, resampling=resampling)
+        _compare(_engine(kind, ctas_per_filter=G), kind, theta, obs, N, 6, draws, resampling=resampling,
+                 exact_particles=(kind == "sv"))
+
+
 def test_fixed_initial_state_and_degenerate_weights():
     """Edge cases: fixed initial state (all particles equal -> CDF ties are uniform steps), and an
     outlier observation that puts almost all weight on a handful of particles."""
