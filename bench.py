@@ -396,7 +396,8 @@ def gpu_arm(args):
                          "algorithmic_bytes_per_launch": bytes_unit * per_gpu_units,
                          "peak_source": peak_src},
             "geometry": {"ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
-                         "block_threads": eng.info("block_threads"), "cooperative": eng.info("cooperative")},
+                         "block_threads": eng.info("block_threads"), "filter_threads": eng.info("filter_threads"),
+                         "cooperative": eng.info("cooperative")},
             "log_like_sample": float(ll[0]),
         }
         if cpu is not None:

@@ -297,7 +297,8 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "ctas_per_filter")) *value = h->prob.G;
   else if (!strcmp(name, "n_groups")) *value = h->prob.n_groups;
   else if (!strcmp(name, "per_cta")) *value = h->prob.per_cta;
-  else if (!strcmp(name, "block_threads")) *value = kBlock;
+  else if (!strcmp(name, "block_threads")) *value = kThreads;  // filter warps + the smoother warpgroup
+  else if (!strcmp(name, "filter_threads")) *value = kBlock;
   else if (!strcmp(name, "chunk")) *value = kBlock * h->items;
   else if (!strcmp(name, "items")) *value = h->items;
   else if (!strcmp(name, "anc_smem")) *value = h->prob.anc_smem;
