@@ -57,7 +57,7 @@ extern "C" {
 /* resampling (resampling.pyx) */
 #define PFB200_RESAMPLE_SYSTEMATIC 0
 #define PFB200_RESAMPLE_STRATIFIED 1
-#define PFB200_RESAMPLE_MULTINOMIAL 2 /* resampling.pyx:33-42; per-particle uniforms like stratified; not for distributed filters */
+#define PFB200_RESAMPLE_MULTINOMIAL 2 /* resampling.pyx:33-42; per-particle uniforms like stratified */
 
 /* flags (bit mask) */
 #define PFB200_FLAG_STORE_HISTORY 1u    /* keep all T+1 generations (particles, log-weights, ancestors) */
@@ -65,6 +65,9 @@ extern "C" {
 #define PFB200_FLAG_SVL_OBS_MODEL 4u    /* SV-leverage: propagate with obs[t-1] (model-consistent, Cython twin)
                                            instead of obs[t] (NumPy twin) */
 #define PFB200_FLAG_INJECT_PER_FILTER 8u /* injected randomness is given per filter ([B][...]) */
+#define PFB200_FLAG_STORE_STATES 16u    /* keep all T+1 generations of the PARTICLES only (the other rings stay
+                                           L+2 deep): enough for `traj` = particles[traj_index, :] (standard.py:104-106)
+                                           at 1/3 of the memory of STORE_HISTORY and without its slower lineage walks */
 
 /* error codes */
 #define PFB200_OK 0
@@ -143,7 +146,9 @@ int pfb200_last_kernel_ms(pfb200_handle* h, float* ms);
  *   smo        [B][T+1]       fixed-lag smoothed means                  standard.py:140-157
  *   grad_terms [B][P][T+1]    G[p][i] = sum_n w_lag[n] d_p log p(x_{i+1}, y_i | x_i)   standard.py:161-169
  *   traj_index [B]            row index of the trajectory draw          standard.py:104-105
- *   traj       [B][T+1]       particles[traj_index, :]; needs PFB200_FLAG_STORE_HISTORY (else NaN)
+ *   traj       [B][T+1]       particles[traj_index, :]; needs PFB200_FLAG_STORE_STATES or _HISTORY (else NaN)
+ * fixed_lag = 0 with do_smoother: smo == filt (zero hops) and grad_terms is returned as zeros (the reference
+ * raises NameError at standard.py:161 when it is asked for score terms with fixed_lag = 0).
  */
 int pfb200_fetch(pfb200_handle* h, double* log_like, double* filt, double* smo, double* grad_terms,
                  int32_t* traj_index, double* traj);
@@ -186,11 +191,27 @@ int pfb200_philox_uniforms(pfb200_handle* h, uint64_t seed, uint64_t eval_id, in
  *   (all-gather the R handle blobs between the processes, e.g. torch.distributed)
  *   pfb200_dist_connect(h, all, R); (host barrier); pfb200_execute(h) on all ranks; pfb200_fetch
  * filt / smo / grad_terms of a rank are its PARTIAL sums (add them over ranks); log_like is complete
- * and identical on every rank; traj_index is -1.
+ * and identical on every rank; traj_index is -1 (see pfb200_dist_traj_* below).
+ *
+ * A connected handle stays connected across pfb200_update_params and across pfb200_configure calls that
+ * keep the geometry (N, T, L, CTAs per rank, world, dtype, smoother, resampling): an MH iteration only
+ * re-uploads theta.  Any other re-configuration needs pfb200_dist_disconnect on EVERY rank (then a host
+ * barrier) first -- a rank must not re-allocate buffers its peers still map.  A device-side abort
+ * (PFB200_ETIMEOUT) disconnects the handle: export / connect again.
  */
 int pfb200_dist_handle_bytes(void);
 int pfb200_dist_export(pfb200_handle* h, void* handles_out, int bytes);
 int pfb200_dist_connect(pfb200_handle* h, const void* all_handles, int world);
+int pfb200_dist_disconnect(pfb200_handle* h);
+/* The same for ranks that live in ONE process (one handle per GPU, peer access instead of IPC; also
+ * several ranks on one device for single-GPU tests of the peer paths): handles[r] must be configured as
+ * rank r of `world`.  Then pfb200_execute(handles[0..world)) in any order, pfb200_fetch on each. */
+int pfb200_dist_connect_local(pfb200_handle* const* handles, int world);
+/* Trajectory draw of a distributed filter (standard.py:104-105): `count` = this rank's part of
+ * k = #{ j : cdf[j] <= u_final }; sum the counts over ranks, then the rank that owns particle
+ * min(k, N-1) returns traj_index = a_T[k] from pfb200_dist_traj_lookup (every other rank: -1). */
+int pfb200_dist_traj_count(pfb200_handle* h, int32_t* count);
+int pfb200_dist_traj_lookup(pfb200_handle* h, int32_t k, int32_t* index);
 
 /* Debug builds (-DPFB_PROFILE) only: per-CTA cycle counters of 12 phases of a time step, summed
  * over the launch; out[cta][12].  Returns the number of CTAs written (or a negative error). */

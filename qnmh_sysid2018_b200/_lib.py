@@ -14,6 +14,7 @@ MODEL_LGSS, MODEL_SV, MODEL_SVL, MODEL_LGSS_FA = 0, 1, 2, 3
 F64, F32 = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 FLAG_STORE_HISTORY, FLAG_OBS_PER_FILTER, FLAG_SVL_OBS_MODEL, FLAG_INJECT_PER_FILTER = 1, 2, 4, 8
+FLAG_STORE_STATES = 16
 ABI_VERSION = 1
 
 _dp = C.POINTER(C.c_double)
@@ -47,6 +48,10 @@ SIGNATURES = {
     "pfb200_dist_handle_bytes": (C.c_int, []),
     "pfb200_dist_export": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "pfb200_dist_connect": (C.c_int, [_H, C.c_void_p, C.c_int]),
+    "pfb200_dist_disconnect": (C.c_int, [_H]),
+    "pfb200_dist_connect_local": (C.c_int, [C.POINTER(_H), C.c_int]),
+    "pfb200_dist_traj_count": (C.c_int, [_H, _ip]),
+    "pfb200_dist_traj_lookup": (C.c_int, [_H, C.c_int32, _ip]),
     "pfb200_debug_profile": (C.c_int, [_H, C.POINTER(C.c_longlong), C.c_int]),
     "pfb200_philox_normals": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),
     "pfb200_philox_uniforms": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp]),

@@ -58,6 +58,8 @@ struct DeviceProblem {
   int RX, RA, RW;  // ring depths: particles, ancestors, log-weights
   int do_smoother, gen_init, resampling, svl_obs_model;
   int inject, inject_per_filter, obs_per_filter, ws_per_filter;
+  int xs_per_filter;  // the state ring is [B][RX][NS] (all generations kept: RX = T+1) while the other rings
+                      // stay per group -- PFB200_FLAG_STORE_STATES, the rows state_trajectory is read from
   double initial_state;
   unsigned long long seed;
   long long spin_limit;
@@ -99,6 +101,7 @@ struct DeviceProblem {
   int* peer_anc[8];
   double* peer_xval[8];
   unsigned* peer_xcount[8];
+  double* peer_cdf[8];  // multinomial resampling: every rank keeps a full copy [N] of the normalised CDF
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -663,7 +666,7 @@ struct PfKernel {
     const int N = p.N, T = p.T, L = p.L;
     const int ws = p.ws_per_filter ? b : q;
     const size_t NS = (size_t)p.NS;
-    const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
+    const Real* xr = reinterpret_cast<const Real*>(p.x_ring) + (size_t)(p.xs_per_filter ? b : ws) * p.RX * NS + p.halo - lo;
     const Real* swr = reinterpret_cast<const Real*>(p.s_ring) + (size_t)ws * 3 * NS + p.halo - lo;  // shifted weights
     const int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
@@ -836,8 +839,19 @@ struct PfKernel {
       PFB_TICK(11);
       if (!own) continue;
       Real xp[4];
+      if (GENERAL && dist && p.resampling == 2) {
+        // multinomial parents of a distributed filter live anywhere: own span / halos, or a peer's ring
+        const int sp = ring_back(sx, 1, p.RX);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) xp[e] = ld_cg(xp_row + (unsigned)j[e]);
+        for (int e = 0; e < 4; ++e) {
+          const int jj = j[e];  // c0 == 0: a global index
+          xp[e] = is_local(jj) ? ld_cg(x_prev + jj)
+                               : ld_sys(peer_row(reinterpret_cast<const Real*>(p.peer_x[jj / p.span]), jj / p.span, sp) + jj);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xp[e] = ld_cg(xp_row + (unsigned)j[e]);
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
         Real z0, z1;
@@ -921,7 +935,7 @@ struct PfKernel {
     const size_t NS = (size_t)p.NS;
     // ring rows are addressed with GLOBAL particle indices: the views are shifted by the first index
     // this rank holds (0 on a single GPU)
-    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)ws * p.RX * NS + p.halo - lo;
+    Real* xr = reinterpret_cast<Real*>(p.x_ring) + (size_t)(p.xs_per_filter ? b : ws) * p.RX * NS + p.halo - lo;
     Real* lwr = reinterpret_cast<Real*>(p.logw) + (size_t)ws * p.RW * NS + p.halo - lo;
     int* ar = p.anc_ring + (size_t)ws * p.RA * NS + p.halo - lo;
     const double* obs = p.obs + (p.obs_per_filter ? (size_t)b * (T + 1) : 0);
@@ -1080,8 +1094,11 @@ struct PfKernel {
           for (int jl = tid; jl < own; jl += BLOCK)
             if (sh_s[jl] <= u) ++traj_cnt;
         } else if (pull) {
-          double* cg = p.cdf_g + (size_t)ws * NS - lo;
-          for (int jl = tid; jl < own; jl += BLOCK) cg[j_begin + jl] = sh_s[jl];
+          // every rank searches the whole CDF: a distributed filter mirrors its part into all ranks' copies
+          for (int r = 0; r < (dist ? p.R : 1); ++r) {
+            double* cg = dist ? p.peer_cdf[r] : p.cdf_g + (size_t)ws * NS;
+            for (int jl = tid; jl < own; jl += BLOCK) cg[j_begin + jl] = sh_s[jl];
+          }
         } else {
           children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
                        y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
@@ -1108,11 +1125,13 @@ struct PfKernel {
               if (jl < len && sh_s[jl] <= u) ++traj_cnt;
             }
           } else if (pull) {
-            double* cg = p.cdf_g + (size_t)ws * NS - lo;
+            for (int r = 0; r < (dist ? p.R : 1); ++r) {
+              double* cg = dist ? p.peer_cdf[r] : p.cdf_g + (size_t)ws * NS;
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-              const int jl = k * BLOCK + tid;
-              if (jl < len) cg[c0 + jl] = sh_s[jl];
+              for (int k = 0; k < ITEMS; ++k) {
+                const int jl = k * BLOCK + tid;
+                if (jl < len) cg[c0 + jl] = sh_s[jl];
+              }
             }
           } else {
             const double next_base = base + chunk_total;
@@ -1132,8 +1151,8 @@ struct PfKernel {
         // every CTA's part of the CDF is published; the children of this CTA's own index range
         // search all of it (resampling.pyx:33-42: unsorted uniforms, ancestors in any tile)
         exchange(0.0);
-        children_chunk(p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
-                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, 0, mx);
+        children_chunk(dist ? p.cdf_g : p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
+                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, p.rank, mx);
       }
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);

@@ -159,9 +159,12 @@ struct pfb200_handle {
   // distributed single filter (one process per GPU, peer memory over NVLink)
   long long opt_dist_world = 1, opt_dist_rank = 0;
   bool dist_connected = false;
+  bool dist_same_device = false;  // ranks of one process on ONE device (single-GPU test of the peer paths):
+                                  // plain launches, co-residency by construction (R * G_loc <= SM count)
   unsigned dist_epoch = 0;
   unsigned dist_sjobs = 0;
-  void* peer_opened[8][5] = {};  // IPC mappings to close
+  void* peer_opened[8][6] = {};  // IPC mappings to close
+  long long dist_geom[8] = {};   // geometry the peer mappings were made for (see dist_geometry)
   // configured problem
   bool configured = false;
   bool executed = false;
@@ -179,10 +182,14 @@ struct pfb200_handle {
   std::vector<unsigned long long> h_evals;
 };
 
+constexpr int kDistBufs = 6;  // exported per rank: particles, log-weights, ancestors, exchange values, counters, CDF copy
+
 static void dist_close(pfb200_handle* h) {
   for (int r = 0; r < 8; ++r)
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < kDistBufs; ++k)
       if (h->peer_opened[r][k]) { cudaIpcCloseMemHandle(h->peer_opened[r][k]); h->peer_opened[r][k] = nullptr; }
+  h->dist_connected = false;
+  h->dist_same_device = false;
 }
 
 extern "C" {
@@ -280,7 +287,11 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
   else if (!strcmp(name, "max_groups")) h->opt_max_groups = value;
   else if (!strcmp(name, "spin_limit")) h->opt_spin_limit = value;
   else if (!strcmp(name, "l2_persist")) h->opt_l2_persist = value;
-  else if (!strcmp(name, "items")) h->opt_items = value;
+  else if (!strcmp(name, "items")) {
+    if (value != 0 && value != kItems && value != kItemsAlt && value != kItemsSmall)
+      return fail(PFB200_EINVAL, "pfb200_set_option: items must be 0 (automatic), %d, %d or %d", kItems, kItemsAlt, kItemsSmall);
+    h->opt_items = value;
+  }
   else if (!strcmp(name, "anc_smem")) h->opt_anc_smem = value;
   else if (!strcmp(name, "dist_world")) {
     if (value < 1 || value > 8) return fail(PFB200_EINVAL, "pfb200_set_option: dist_world must be 1..8");
@@ -310,7 +321,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "blocks_per_sm")) *value = h->blocks_per_sm;
   else if (!strcmp(name, "cooperative")) *value = h->cooperative ? 1 : 0;
   else if (!strcmp(name, "smem_bytes")) *value = (long long)h->smem_bytes;
-  else if (!strcmp(name, "kernel_launches_per_execute")) *value = 3 + ((h->flags & PFB200_FLAG_STORE_HISTORY) ? 1 : 0);
+  else if (!strcmp(name, "kernel_launches_per_execute")) *value = 3 + ((h->flags & (PFB200_FLAG_STORE_HISTORY | PFB200_FLAG_STORE_STATES)) ? 1 : 0);
   else if (!strcmp(name, "workspace_bytes")) {
     *value = (long long)(h->x_ring.cap + h->logw.cap + h->anc.cap + h->filt_part.cap + h->smo_part.cap);
   } else return fail(PFB200_EINVAL, "pfb200_get_info: unknown key '%s'", name);
@@ -355,8 +366,9 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   if (B < 1 || N < 1 || T < 1 || L < 0)
     return fail(PFB200_EINVAL, "pfb200_configure: need n_filters>=1, no_particles>=1, no_obs>=1, fixed_lag>=0 (got %d,%d,%d,%d)", B, N, T, L);
   if (N > (1 << 30)) return fail(PFB200_EINVAL, "pfb200_configure: no_particles %d exceeds 2^30", N);
-  if (do_smoother && L < 1)
-    return fail(PFB200_EINVAL, "pfb200_configure: the fixed-lag smoother needs fixed_lag >= 1 (the reference raises NameError at standard.py:161 for fixed_lag=0)");
+  // fixed_lag = 0 with the smoother: zero hops, smo == filt (standard.py:146-157); the score terms of such a
+  // run are undefined (the reference raises NameError at standard.py:161 when it is asked for them) and are
+  // returned as zeros
   if (resampling != PFB200_RESAMPLE_SYSTEMATIC && resampling != PFB200_RESAMPLE_STRATIFIED &&
       resampling != PFB200_RESAMPLE_MULTINOMIAL)
     return fail(PFB200_EINVAL, "pfb200_configure: unsupported resampling method %d", resampling);
@@ -366,6 +378,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     return fail(PFB200_EINVAL, "pfb200_configure: injected randomness needs all of inj_z0, inj_u, inj_z, inj_u_final");
   const bool inject = n_inj == 4;
   const bool history = (flags & PFB200_FLAG_STORE_HISTORY) != 0;
+  const bool states = !history && (flags & PFB200_FLAG_STORE_STATES) != 0;
   CUDA_TRY(cudaSetDevice(h->device));
 
   bool general = inject || resampling != PFB200_RESAMPLE_SYSTEMATIC;  // + the distributed filter (below)
@@ -376,13 +389,10 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const int R = (int)h->opt_dist_world, rank = (int)h->opt_dist_rank;
   if (R > 1) {
     if (rank < 0 || rank >= R) return fail(PFB200_EINVAL, "pfb200_configure: dist_rank %d out of range for dist_world %d", rank, R);
-    if (resampling == PFB200_RESAMPLE_MULTINOMIAL)
-      return fail(PFB200_EINVAL, "pfb200_configure: multinomial resampling is not available for a distributed filter");
-    if (B != 1 || history)
-      return fail(PFB200_EINVAL, "pfb200_configure: a distributed filter takes n_filters = 1 and no STORE_HISTORY");
+    if (B != 1 || history || states)
+      return fail(PFB200_EINVAL, "pfb200_configure: a distributed filter takes n_filters = 1 and no STORE_HISTORY / STORE_STATES");
     general = true;  // the peer-memory paths live in the general flavour
   }
-  h->dist_connected = false;
   int G = 1, G_loc = 1, per = N, n_groups = 1, tile_cap = kChunk, capacity = 0, bps = 0, n_chunks = 1;
   size_t smem = 0;
   // Two tile granularities are compiled (ITEMS = 7 / 9 parents per thread and scan sub-chunk): take
@@ -450,6 +460,21 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   h->smem_bytes = smem;
   h->n_ws = history ? B : n_groups;
 
+  // A connected distributed handle keeps its peer mappings (and the running exchange counters) as long
+  // as the geometry the mappings were made for is unchanged: an MH iteration re-configures / updates
+  // parameters without touching the IPC handles.  Any other change needs pfb200_dist_disconnect on every
+  // rank first (peers must not keep mappings of buffers this rank is about to re-allocate).
+  const long long geom[8] = {N, T, L, G_loc, R, rank, (long long)h->dtype * 4 + (do_smoother ? 2 : 0) + (resampling == PFB200_RESAMPLE_MULTINOMIAL ? 1 : 0), items};
+  bool keep_peers = false;
+  if (h->dist_connected) {
+    keep_peers = R > 1 && !memcmp(geom, h->dist_geom, sizeof(geom));
+    if (!keep_peers)
+      return fail(PFB200_ESTATE, "pfb200_configure: this distributed handle is connected to its peers; call "
+                                 "pfb200_dist_disconnect on every rank (then a host barrier) before changing its geometry");
+  }
+  memcpy(h->dist_geom, geom, sizeof(geom));
+  const DeviceProblem old = h->prob;
+
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
   p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
@@ -458,7 +483,8 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   // states and ancestors: lineage walks across a rank boundary stay in local memory)
   p.halo = R > 1 ? (p.span < (1 << 17) ? p.span : (1 << 17)) : 0;
   if (R > 1) p.NS = p.span + 2 * p.halo;
-  p.RX = history ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
+  p.RX = (history || states) ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
+  p.xs_per_filter = states ? 1 : 0;
   p.RA = history ? T + 1 : L + 2;
   p.RW = history ? T + 1 : 3;
   p.do_smoother = do_smoother ? 1 : 0;
@@ -492,11 +518,12 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     CUDA_TRY(h->inj_z.reserve(n_injr * T1 * N * 8));
     CUDA_TRY(h->inj_uf.reserve(n_injr * 8));
   }
-  CUDA_TRY(h->x_ring.reserve((size_t)h->n_ws * p.RX * p.NS * real_sz));
+  CUDA_TRY(h->x_ring.reserve((size_t)(states ? B : h->n_ws) * p.RX * p.NS * real_sz));
   CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
   CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
   if (do_smoother) CUDA_TRY(h->s_ring.reserve((size_t)h->n_ws * 3 * p.NS * real_sz));
-  if (resampling == PFB200_RESAMPLE_MULTINOMIAL) CUDA_TRY(h->cdf_g.reserve((size_t)h->n_ws * p.NS * 8));
+  if (resampling == PFB200_RESAMPLE_MULTINOMIAL)  // distributed: every rank keeps a copy of the WHOLE CDF
+    CUDA_TRY(h->cdf_g.reserve(R > 1 ? ((size_t)N + 32) * 8 : (size_t)h->n_ws * p.NS * 8));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
   CUDA_TRY(h->xcount.reserve((size_t)n_groups * 32 * 4));
   CUDA_TRY(h->abortf.reserve(16));
@@ -536,7 +563,12 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.s_ring = h->s_ring.ptr;
   p.traj_idx = h->traj_idx.as<int>();
   p.prof = h->prof.as<long long>();
-  for (int r = 0; r < 8; ++r) { p.peer_x[r] = p.x_ring; p.peer_lw[r] = p.logw; p.peer_anc[r] = p.anc_ring; p.peer_xval[r] = p.xval; p.peer_xcount[r] = p.xcount; }
+  for (int r = 0; r < 8; ++r) { p.peer_x[r] = p.x_ring; p.peer_lw[r] = p.logw; p.peer_anc[r] = p.anc_ring; p.peer_xval[r] = p.xval; p.peer_xcount[r] = p.xcount; p.peer_cdf[r] = p.cdf_g; }
+  if (keep_peers) {
+    if (p.x_ring != old.x_ring || p.logw != old.logw || p.anc_ring != old.anc_ring || p.xval != old.xval || p.xcount != old.xcount || p.cdf_g != old.cdf_g)
+      return fail(PFB200_ESTATE, "pfb200_configure: internal error: a connected distributed handle re-allocated exported buffers");
+    for (int r = 0; r < 8; ++r) { p.peer_x[r] = old.peer_x[r]; p.peer_lw[r] = old.peer_lw[r]; p.peer_anc[r] = old.peer_anc[r]; p.peer_xval[r] = old.peer_xval[r]; p.peer_xcount[r] = old.peer_xcount[r]; p.peer_cdf[r] = old.peer_cdf[r]; }
+  }
 
   // ---- uploads
   CUDA_TRY(cudaMemcpyAsync(h->obs.ptr, obs, n_obs_rows * T1 * 8, cudaMemcpyHostToDevice, h->stream));
@@ -568,7 +600,8 @@ int pfb200_execute(pfb200_handle* h) {
   if (p.R > 1) {
     if (!h->dist_connected) return fail(PFB200_ESTATE, "pfb200_execute: distributed filter is not connected (pfb200_dist_connect)");
     p.epoch0 = h->dist_epoch;               // peer counters keep counting across launches
-    h->dist_epoch += 2u * (unsigned)p.T + 3u;  // exchanges per launch: init + 2 per step + 2 at the end
+    // exchanges per launch: init + 2 per step + 2 at the end (+ 1 per step: the CDF barrier of multinomial resampling)
+    h->dist_epoch += 2u * (unsigned)p.T + 3u + (p.resampling == PFB200_RESAMPLE_MULTINOMIAL ? (unsigned)p.T : 0u);
     p.sjobs0 = h->dist_sjobs;               // smoother jobs per CTA and launch: lag times L..T-1 + the tail
     if (p.do_smoother) h->dist_sjobs += (unsigned)(p.T > p.L ? p.T - p.L : 0) + 1u;
   } else {
@@ -577,13 +610,14 @@ int pfb200_execute(pfb200_handle* h) {
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
   const dim3 grid(p.n_groups * p.G_loc), block(kThreads);
-  {
-    // The ancestor ring is re-read every time step for L steps (fixed-lag lineage walks) while
-    // particles and log-weights stream through: keep it resident in L2.
+  if (h->opt_l2_persist && h->stream == h->own_stream && p.do_smoother && h->l2_persist_max > 0 && h->l2_window_max > 0) {
+    // Tuning option (off by default, and never applied to a caller-supplied stream whose own access
+    // policy window it would clobber): pin the ancestor ring -- re-read every time step for L steps by
+    // the lineage walks -- in the persisting part of L2.
     const size_t anc_bytes = (size_t)h->n_ws * p.RA * p.NS * 4;
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
-    if (h->opt_l2_persist && p.do_smoother && h->l2_persist_max > 0 && h->l2_window_max > 0) {
+    {
       size_t win = anc_bytes < h->l2_window_max ? anc_bytes : h->l2_window_max;
       size_t set_aside = win < h->l2_persist_max ? win : h->l2_persist_max;
       CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
@@ -596,7 +630,7 @@ int pfb200_execute(pfb200_handle* h) {
     CUDA_TRY(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   }
   CUDA_TRY(cudaEventRecord(h->evk0, h->stream));
-  if (h->cooperative) {
+  if (h->cooperative && !h->dist_same_device) {
     void* args[] = {&p};
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)h->kernel, grid, block, args, h->smem_bytes, h->stream));
   } else {
@@ -613,7 +647,7 @@ int pfb200_execute(pfb200_handle* h) {
   CUDA_TRY(cudaGetLastError());
   pf_loglike_kernel<<<p.B, 256, 0, h->stream>>>(fa.ll_terms, fa.log_like, (int)T1);
   CUDA_TRY(cudaGetLastError());
-  if (h->flags & PFB200_FLAG_STORE_HISTORY) {
+  if (h->flags & (PFB200_FLAG_STORE_HISTORY | PFB200_FLAG_STORE_STATES)) {  // state ring = all T+1 generations
     if (h->dtype == PFB200_F64)
       pf_trajectory_kernel<double><<<p.B, 256, 0, h->stream>>>(h->x_ring.as<double>(), p.traj_idx, h->traj.as<double>(), p.NS, (int)T1);
     else
@@ -633,7 +667,12 @@ int pfb200_synchronize(pfb200_handle* h) {
   if (h->executed) {
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, h->abortf.ptr, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(PFB200_ETIMEOUT, "pfb200: device-side abort: an inter-CTA exchange exceeded spin_limit");
+    if (flag) {
+      // the peer counters of a distributed filter are out of step after an abort: force a fresh
+      // export / connect (dist_export resets the counters)
+      if (h->prob.R > 1) dist_close(h);
+      return fail(PFB200_ETIMEOUT, "pfb200: device-side abort: an inter-CTA exchange exceeded spin_limit");
+    }
   }
   return PFB200_OK;
 }
@@ -676,7 +715,7 @@ int pfb200_fetch(pfb200_handle* h, double* log_like, double* filt, double* smo, 
     if ((rc = d2h(h, grad_terms, h->grad.ptr, B * p.P * T1 * 8))) return rc;
   }
   if ((rc = d2h(h, traj_index, h->traj_idx.ptr, B * 4))) return rc;
-  const bool history = (h->flags & PFB200_FLAG_STORE_HISTORY) != 0;
+  const bool history = (h->flags & (PFB200_FLAG_STORE_HISTORY | PFB200_FLAG_STORE_STATES)) != 0;
   if (history && (rc = d2h(h, traj, h->traj.ptr, B * T1 * 8))) return rc;
   rc = pfb200_synchronize(h);
   if (rc) return rc;
@@ -684,6 +723,8 @@ int pfb200_fetch(pfb200_handle* h, double* log_like, double* filt, double* smo, 
     if (smo) for (size_t i = 0; i < B * T1; ++i) smo[i] = 0.0;
     if (grad_terms) for (size_t i = 0; i < B * p.P * T1; ++i) grad_terms[i] = 0.0;
   }
+  if (p.do_smoother && p.L == 0 && grad_terms)  // zero hops: score terms are undefined (see pfb200_configure)
+    for (size_t i = 0; i < B * p.P * T1; ++i) grad_terms[i] = 0.0;
   if (!history && traj) for (size_t i = 0; i < B * T1; ++i) traj[i] = NAN;
   return PFB200_OK;
 }
@@ -747,7 +788,7 @@ int pfb200_run(pfb200_handle* h, int n_filters, int no_particles, int no_obs, in
 
 // ---- distributed single filter: exchange of CUDA IPC handles between the per-GPU processes ----
 
-int pfb200_dist_handle_bytes(void) { return 5 * (int)sizeof(cudaIpcMemHandle_t); }
+int pfb200_dist_handle_bytes(void) { return kDistBufs * (int)sizeof(cudaIpcMemHandle_t); }
 
 int pfb200_dist_export(pfb200_handle* h, void* out, int bytes) {
   if (!h || !out || !h->configured) return fail(PFB200_ESTATE, "pfb200_dist_export: configure first");
@@ -755,10 +796,12 @@ int pfb200_dist_export(pfb200_handle* h, void* out, int bytes) {
   if (bytes < pfb200_dist_handle_bytes()) return fail(PFB200_EINVAL, "pfb200_dist_export: buffer too small");
   CUDA_TRY(cudaSetDevice(h->device));
   dist_close(h);
-  h->dist_connected = false;
   cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(out);
-  void* ptrs[5] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr};
-  for (int k = 0; k < 5; ++k) CUDA_TRY(cudaIpcGetMemHandle(&hs[k], ptrs[k]));
+  memset(hs, 0, (size_t)pfb200_dist_handle_bytes());
+  void* ptrs[kDistBufs] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr,
+                           h->prob.resampling == PFB200_RESAMPLE_MULTINOMIAL ? h->cdf_g.ptr : nullptr};
+  for (int k = 0; k < kDistBufs; ++k)
+    if (ptrs[k]) CUDA_TRY(cudaIpcGetMemHandle(&hs[k], ptrs[k]));
   // fresh counters; the caller synchronises all ranks (host barrier) between connect and execute
   CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
   h->dist_epoch = 0;
@@ -772,18 +815,97 @@ int pfb200_dist_connect(pfb200_handle* h, const void* all_handles, int world) {
   if (world != p.R) return fail(PFB200_EINVAL, "pfb200_dist_connect: world %d != configured dist_world %d", world, p.R);
   CUDA_TRY(cudaSetDevice(h->device));
   const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
-  void* own[5] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr};
+  const bool cdf = p.resampling == PFB200_RESAMPLE_MULTINOMIAL;
+  void* own[kDistBufs] = {h->x_ring.ptr, h->logw.ptr, h->anc.ptr, h->xval.ptr, h->xcount.ptr, h->cdf_g.ptr};
   for (int r = 0; r < world; ++r) {
-    void* ptr[5];
-    for (int k = 0; k < 5; ++k) {
-      if (r == p.rank) { ptr[k] = own[k]; continue; }
-      CUDA_TRY(cudaIpcOpenMemHandle(&ptr[k], hs[r * 5 + k], cudaIpcMemLazyEnablePeerAccess));
+    void* ptr[kDistBufs];
+    for (int k = 0; k < kDistBufs; ++k) {
+      if (r == p.rank || (k == 5 && !cdf)) { ptr[k] = own[k]; continue; }
+      CUDA_TRY(cudaIpcOpenMemHandle(&ptr[k], hs[r * kDistBufs + k], cudaIpcMemLazyEnablePeerAccess));
       h->peer_opened[r][k] = ptr[k];
     }
     p.peer_x[r] = ptr[0]; p.peer_lw[r] = ptr[1]; p.peer_anc[r] = reinterpret_cast<int*>(ptr[2]);
     p.peer_xval[r] = reinterpret_cast<double*>(ptr[3]); p.peer_xcount[r] = reinterpret_cast<unsigned*>(ptr[4]);
+    p.peer_cdf[r] = reinterpret_cast<double*>(ptr[5]);
   }
   h->dist_connected = true;
+  return PFB200_OK;
+}
+
+int pfb200_dist_connect_local(pfb200_handle* const* handles, int world) {
+  if (!handles || world < 2 || world > 8) return fail(PFB200_EINVAL, "pfb200_dist_connect_local: need 2..8 handles");
+  for (int r = 0; r < world; ++r) {
+    pfb200_handle* h = handles[r];
+    if (!h || !h->configured) return fail(PFB200_ESTATE, "pfb200_dist_connect_local: configure every handle first");
+    if (h->prob.R != world || h->prob.rank != r)
+      return fail(PFB200_EINVAL, "pfb200_dist_connect_local: handle %d is configured as rank %d of %d", r, h->prob.rank, h->prob.R);
+    if (memcmp(h->dist_geom, handles[0]->dist_geom, 5 * sizeof(long long)) || h->dtype != handles[0]->dtype)
+      return fail(PFB200_EINVAL, "pfb200_dist_connect_local: handle %d has a different geometry", r);
+  }
+  bool same_device = true;
+  for (int r = 1; r < world; ++r) same_device = same_device && handles[r]->device == handles[0]->device;
+  if (same_device && (long long)world * handles[0]->prob.G_loc > (long long)handles[0]->blocks_per_sm * handles[0]->num_sms)
+    return fail(PFB200_EINVAL, "pfb200_dist_connect_local: %d ranks x %d CTAs on one device are not co-resident", world, handles[0]->prob.G_loc);
+  for (int r = 0; r < world; ++r) {
+    pfb200_handle* h = handles[r];
+    CUDA_TRY(cudaSetDevice(h->device));
+    dist_close(h);
+    for (int q = 0; q < world; ++q) {
+      pfb200_handle* o = handles[q];
+      if (o->device != h->device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+        if (!can) return fail(PFB200_ECUDA, "pfb200_dist_connect_local: device %d cannot access device %d", h->device, o->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+        (void)cudaGetLastError();
+      }
+      DeviceProblem& p = h->prob;
+      p.peer_x[q] = o->x_ring.ptr; p.peer_lw[q] = o->logw.ptr; p.peer_anc[q] = o->anc.as<int>();
+      p.peer_xval[q] = o->xval.as<double>(); p.peer_xcount[q] = o->xcount.as<unsigned>(); p.peer_cdf[q] = o->cdf_g.as<double>();
+    }
+    CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
+    h->dist_epoch = 0;
+    h->dist_sjobs = 0;
+  }
+  for (int r = 0; r < world; ++r) {
+    CUDA_TRY(cudaSetDevice(handles[r]->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    handles[r]->dist_connected = true;
+    handles[r]->dist_same_device = same_device;
+  }
+  return PFB200_OK;
+}
+
+int pfb200_dist_disconnect(pfb200_handle* h) {
+  if (!h) return fail(PFB200_EINVAL, "pfb200_dist_disconnect: NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  dist_close(h);
+  return PFB200_OK;
+}
+
+int pfb200_dist_traj_count(pfb200_handle* h, int32_t* count) {
+  if (!h || !count || !h->executed) return fail(PFB200_ESTATE, "pfb200_dist_traj_count: nothing executed yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(count, h->traj_k.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return PFB200_OK;
+}
+
+int pfb200_dist_traj_lookup(pfb200_handle* h, int32_t k, int32_t* index) {
+  if (!h || !index || !h->executed) return fail(PFB200_ESTATE, "pfb200_dist_traj_lookup: nothing executed yet");
+  const DeviceProblem& p = h->prob;
+  *index = -1;
+  if (k < 0) return fail(PFB200_EINVAL, "pfb200_dist_traj_lookup: k < 0");
+  if (k > p.N - 1) k = p.N - 1;
+  const long long lo = (long long)p.rank * p.span;
+  if (k < lo || k >= lo + p.span) return PFB200_OK;  // another rank owns particle k
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // generation T lives in slot T mod RA of the ancestor ring; rows are [halo | own span | halo]
+  const size_t off = (size_t)(p.T % p.RA) * p.NS + p.halo + (size_t)(k - lo);
+  CUDA_TRY(cudaMemcpy(index, h->anc.as<int>() + off, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return PFB200_OK;
 }
 

@@ -1,17 +1,26 @@
 """ONE particle filter sharded over the GPUs of a box (BASELINE config C5).
 
-One process per GPU (`torch.distributed`).  Rank r holds the particles with global indices
-[r*span, (r+1)*span).  Inside the persistent kernel every CTA pushes its children to the owner of
-their index range with NVLink peer stores, and the two per-step exchanges (CDF tile totals, max
-log-weight) are all-gathers through peer memory with system-scope release/acquire -- no NCCL call
-sits on the data path.  `torch.distributed` is only the control plane: it carries the CUDA IPC
-handles between the processes once per configuration and sums the per-rank partial results
-((P+2)(T+1) doubles) at the end.
+Rank r holds the particles with global indices [r*span, (r+1)*span).  Inside the persistent kernel
+every CTA pushes its children to the owner of their index range with NVLink peer stores, and the
+per-step exchanges (CDF tile totals, max log-weight) are all-gathers through peer memory with
+system-scope release/acquire -- no NCCL call sits on the data path.
+
+Two hosts for the same kernels:
+
+* `DistributedParticleFilter` -- one process per GPU (`torch.distributed`), CUDA IPC handles.
+  `torch.distributed` is only the control plane: it carries the IPC handles between the processes
+  ONCE per geometry and sums the per-rank partial results ((P+2)(T+1) doubles) at the end.  The
+  peer mappings and exchange counters stay alive across evaluations: an MH iteration is
+  `prepare()` (= `update_params` when only theta / the random stream changed) + `execute()`.
+* `LocalShardedParticleFilter` -- all ranks in ONE process (one handle per device, peer access); also
+  several ranks on one device, which is how the single-GPU test tier exercises the peer paths.
 
 Random numbers are keyed by the GLOBAL particle index, and the CDF tiling depends only on the total
 number of CTAs, so the result equals a single-GPU run with `ctas_per_filter = world * ctas_per_rank`
-(checked by tests/test_gpu_distributed.py)."""
+(checked by tests/test_gpu_distributed.py and tests/test_gpu_configs.py)."""
 import numpy as np
+
+_PARTIAL_KEYS = ("filt", "smo", "grad_terms")
 
 
 class DistributedParticleFilter(object):
@@ -30,40 +39,136 @@ class DistributedParticleFilter(object):
         if ctas_per_rank:
             self.engine.set_option("ctas_per_filter", ctas_per_rank)
         self.device = device
+        self._key = None
+        self._obs = None
 
     def prepare(self, obs, theta, no_particles, fixed_lag, do_smoother=True,
-                generate_initial_state=True, initial_state=0.0, seed=87655678, eval_id=0):
-        """Configures every rank for N_global particles and connects the peer memory."""
+                generate_initial_state=True, initial_state=0.0, seed=87655678, eval_id=0,
+                resampling="systematic"):
+        """Configures every rank for N_global particles and connects the peer memory.  With an
+        unchanged geometry and data only theta / the stream id are re-uploaded (no IPC traffic,
+        no host barrier)."""
         import torch.distributed as dist
+        obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(-1))
+        key = (int(no_particles), len(obs), int(fixed_lag), bool(do_smoother), bool(generate_initial_state),
+               float(initial_state), resampling)
+        if key == self._key and np.array_equal(obs, self._obs):
+            self.engine.update_params(theta, seed=seed, eval_ids=[eval_id])
+            return
+        if self._key is not None:  # peers must drop their mappings before anyone re-allocates
+            self.engine.dist_disconnect()
+            dist.barrier()
+        self._key = None
         self.engine.configure(obs, theta, no_particles, fixed_lag, do_smoother, generate_initial_state,
-                              initial_state, "systematic", seed=seed, eval_ids=[eval_id])
+                              initial_state, resampling, seed=seed, eval_ids=[eval_id])
         blobs = [None] * self.world
         dist.all_gather_object(blobs, self.engine.dist_export())
         self.engine.dist_connect(b"".join(blobs), self.world)
         dist.barrier()  # every counter is zero and mapped before any rank launches
+        self._key, self._obs = key, obs.copy()
 
     def execute(self):
         self.engine.execute()
 
-    def fetch(self):
-        """Sums the per-rank partial sums; returns the same dict as `Engine.fetch` on every rank."""
+    def fetch(self, trajectory_index=True):
+        """Sums the per-rank partial sums; returns the same dict as `Engine.fetch` on every rank.
+        `traj_index` (standard.py:104-105) is resolved across ranks: the per-rank counts of CDF entries
+        <= u_final add up to k, and the owner of particle k reads a_T[k]."""
         import torch
         import torch.distributed as dist
         out = self.engine.fetch()
-        parts = [out["filt"].ravel(), out["smo"].ravel(), out["grad_terms"].ravel()]
+        k_loc = float(self.engine.dist_traj_count()) if trajectory_index else 0.0
+        parts = [out[k].ravel() for k in _PARTIAL_KEYS] + [np.array([k_loc])]
         flat = torch.from_numpy(np.concatenate(parts))
-        if dist.get_backend() == "nccl":
+        on_gpu = dist.get_backend() == "nccl"
+        if on_gpu:
             flat = flat.cuda(self.device)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat = flat.cpu().numpy()
         o = 0
-        for key in ("filt", "smo", "grad_terms"):
+        for key in _PARTIAL_KEYS:
             n = out[key].size
             out[key] = flat[o:o + n].reshape(out[key].shape).copy()
             o += n
+        if trajectory_index:
+            idx = torch.tensor([self.engine.dist_traj_lookup(int(round(flat[o])))], dtype=torch.int64)
+            if on_gpu:
+                idx = idx.cuda(self.device)
+            dist.all_reduce(idx, op=dist.ReduceOp.MAX)
+            out["traj_index"][0] = int(idx.item())
         return out
 
     def run(self, *args, **kwargs):
         self.prepare(*args, **kwargs)
         self.execute()
         return self.fetch()
+
+    def close(self):
+        if self._key is not None:
+            self.engine.dist_disconnect()
+            self._key = None
+        self.engine.close()
+
+
+class LocalShardedParticleFilter(object):
+    """All ranks of a sharded filter driven from this process: `devices[r]` hosts rank r (repeat a
+    device ordinal to put several ranks on one GPU; their CTAs must be co-resident)."""
+
+    def __init__(self, model_kind="lgss", dtype="float64", devices=(0, 0), ctas_per_rank=0):
+        from .engine import Engine
+        self.world = len(devices)
+        self.engines = []
+        for r, dev in enumerate(devices):
+            eng = Engine(model_kind, dtype, dev)
+            eng.set_option("dist_world", self.world)
+            eng.set_option("dist_rank", r)
+            if ctas_per_rank:
+                eng.set_option("ctas_per_filter", ctas_per_rank)
+            self.engines.append(eng)
+        self._key = None
+
+    def prepare(self, obs, theta, no_particles, fixed_lag, do_smoother=True, generate_initial_state=True,
+                initial_state=0.0, seed=87655678, eval_id=0, resampling="systematic"):
+        from .engine import Engine
+        obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(-1))
+        key = (int(no_particles), obs.tobytes(), int(fixed_lag), bool(do_smoother), bool(generate_initial_state),
+               float(initial_state), resampling)
+        if key == self._key:
+            for eng in self.engines:
+                eng.update_params(theta, seed=seed, eval_ids=[eval_id])
+            return
+        if self._key is not None:
+            for eng in self.engines:
+                eng.dist_disconnect()
+        self._key = None
+        for eng in self.engines:
+            eng.configure(obs, theta, no_particles, fixed_lag, do_smoother, generate_initial_state,
+                          initial_state, resampling, seed=seed, eval_ids=[eval_id])
+        Engine.dist_connect_local(self.engines)
+        self._key = key
+
+    def execute(self):
+        for eng in self.engines:  # asynchronous launches: the ranks run concurrently
+            eng.execute()
+
+    def fetch(self):
+        outs = [eng.fetch() for eng in self.engines]
+        out = outs[0]
+        for key in _PARTIAL_KEYS:
+            out[key] = np.sum([o[key] for o in outs], axis=0)
+        k = sum(eng.dist_traj_count() for eng in self.engines)
+        out["traj_index"][0] = max(eng.dist_traj_lookup(k) for eng in self.engines)
+        out["log_like_per_rank"] = np.array([o["log_like"][0] for o in outs])
+        return out
+
+    def run(self, *args, **kwargs):
+        self.prepare(*args, **kwargs)
+        self.execute()
+        return self.fetch()
+
+    def close(self):
+        for eng in self.engines:
+            if self._key is not None:
+                eng.dist_disconnect()
+            eng.close()
+        self._key = None

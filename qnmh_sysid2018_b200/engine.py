@@ -66,7 +66,8 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def configure(self, obs, theta, no_particles, fixed_lag=0, do_smoother=True,
                   generate_initial_state=True, initial_state=0.0, resampling="systematic",
-                  seed=0, eval_ids=None, draws=None, store_history=False, svl_obs_model=False):
+                  seed=0, eval_ids=None, draws=None, store_history=False, svl_obs_model=False,
+                  store_states=False):
         """obs: (T+1,) shared or (B, T+1); theta: (P,) or (B, P).  `draws`: injected randomness,
         an object with z0 (N,), u (T+1,) [(T+1,N) stratified], z (T+1,N), u_final -- or a list of B
         such objects (one per filter)."""
@@ -86,6 +87,8 @@ class Engine(object):
         N = int(no_particles)
         if store_history:
             flags |= L.FLAG_STORE_HISTORY
+        elif store_states:  # all generations of the particles only (state_trajectory rows)
+            flags |= L.FLAG_STORE_STATES
         if svl_obs_model:
             flags |= L.FLAG_SVL_OBS_MODEL
         z0 = u = z = uf = None
@@ -115,7 +118,7 @@ class Engine(object):
             C.c_uint64(int(seed)), None if ev is None else ev.ctypes.data_as(C.POINTER(C.c_uint64)),
             _dptr(z0), _dptr(u), _dptr(z), _dptr(uf)))
         self._cfg = dict(B=B, N=N, T=T, L=int(fixed_lag), do_smoother=bool(do_smoother),
-                         history=bool(store_history))
+                         history=bool(store_history), states=bool(store_states))
         return self
 
     def update_params(self, theta, seed=0, eval_ids=None):
@@ -125,6 +128,8 @@ class Engine(object):
         ev = None
         if eval_ids is not None:
             ev = np.ascontiguousarray(np.asarray(eval_ids, dtype=np.uint64))
+            if ev.shape != (self._cfg["B"],):
+                raise ValueError("eval_ids must have shape (B,)")
         L.check(self._lib.pfb200_update_params(
             self._h, _dptr(theta), C.c_uint64(int(seed)),
             None if ev is None else ev.ctypes.data_as(C.POINTER(C.c_uint64))))
@@ -199,6 +204,25 @@ class Engine(object):
     def dist_connect(self, all_handles, world):
         buf = C.create_string_buffer(all_handles, len(all_handles))
         L.check(self._lib.pfb200_dist_connect(self._h, buf, int(world)))
+
+    def dist_disconnect(self):
+        L.check(self._lib.pfb200_dist_disconnect(self._h))
+
+    @staticmethod
+    def dist_connect_local(engines):
+        """Connects the rank handles of ONE process (engines[r] configured as rank r)."""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        L.check(engines[0]._lib.pfb200_dist_connect_local(arr, len(engines)))
+
+    def dist_traj_count(self):
+        v = C.c_int32()
+        L.check(self._lib.pfb200_dist_traj_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    def dist_traj_lookup(self, k):
+        v = C.c_int32()
+        L.check(self._lib.pfb200_dist_traj_lookup(self._h, int(k), C.byref(v)))
+        return int(v.value)
 
     def debug_profile(self, max_ctas=4096):
         """(n_ctas, 12) cycle counters per phase; all zero unless built with -DPFB_PROFILE."""

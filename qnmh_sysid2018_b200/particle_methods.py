@@ -14,10 +14,25 @@ Semantics follow the NumPy twin (SURVEY.md section 8 a-Q): lag = min(i+L, T) (Q4
 score term is computed (Q6), `results` is an instance dict (Q12).  Switches for the documented
 divergences: settings['compat'] = 'numpy' | 'cython' selects the Hessian formula (Q7);
 settings['svl_obs_index'] = 'numpy' | 'model' the observation the leverage term reads (Q10).
+
+`results['state_trajectory']` is the reference's row of the particle matrix, `particles[a_T[k], :]`
+(standard.py:104-106, Q9).  It needs every generation of the particles: settings['store_states'] =
+'auto' (default) keeps them on the device when (T+1) * N * 8 bytes fit `STATE_HISTORY_BUDGET`
+(2 GiB; every configuration of the reference's scripts is a few MB), True always, False never; when
+they are not kept the field is NaN and a warning says so -- never a different estimator.
+
+Random streams: a run draws from the Philox stream (settings['seed'] + settings['seed_offset'],
+eval_id) where `eval_id` counts the evaluations of THIS estimator instance (0, 1, 2, ...).  Two
+instances with the same seed replay the same noise; give replicates / parallel chains distinct
+`seed_offset`s, as the reference's scripts do with `np.random.seed(87655678 + seed_offset)`
+(helper_linear_gaussian.py:33).
 """
+import warnings
 from collections import OrderedDict
 
 import numpy as np
+
+STATE_HISTORY_BUDGET = 2 << 30  # bytes of particle history 'store_states': 'auto' accepts
 
 from .models import model_kind_of
 
@@ -82,7 +97,9 @@ class ParticleMethodsB200(object):
                          'device': -1,            # CUDA device ordinal, -1 = current
                          'rng': 'philox',         # 'philox' | 'injected' (self.draws)
                          'seed': 87655678,        # helper_linear_gaussian.py:33
+                         'seed_offset': 0,        # added to the seed (replicates / parallel chains)
                          'store_history': False,  # keep (T+1, N) particles/weights/ancestors
+                         'store_states': 'auto',  # keep (T+1, N) particles only (state_trajectory rows)
                          'compat': 'numpy',       # Hessian formula: 'numpy' | 'cython'
                          'svl_obs_index': 'numpy',  # leverage term reads obs[t] | 'model': obs[t-1]
                          # 'bootstrap' (the reference's filter) | 'fully_adapted' (optimal proposal,
@@ -133,20 +150,26 @@ class ParticleMethodsB200(object):
         injected = s['rng'] == 'injected'
         if injected and self.draws is None:
             raise ValueError("settings['rng']='injected' needs self.draws")
+        states = s['store_states']
+        if states == 'auto':
+            states = len(obs) * int(s['no_particles']) * 8 <= STATE_HISTORY_BUDGET
+        states = bool(states) and not s['store_history']
+        self._have_rows = bool(s['store_history']) or states
         cfg_key = (kind, obs.tobytes(), s['no_particles'], s['fixed_lag'], do_smoother,
                    s['generate_initial_state'], float(s['initial_state']), s['resampling_method'],
-                   s['store_history'], s['svl_obs_index'], injected)
+                   s['store_history'], states, s['svl_obs_index'], injected)
         eval_id = self.eval_id
         self.eval_id += 1
+        seed = int(s['seed']) + int(s['seed_offset'])
         if injected or cfg_key != self._cfg_key:
             engine.configure(obs, theta, s['no_particles'], s['fixed_lag'], do_smoother,
                              s['generate_initial_state'], s['initial_state'], s['resampling_method'],
-                             seed=s['seed'], eval_ids=[eval_id], draws=self.draws if injected else None,
+                             seed=seed, eval_ids=[eval_id], draws=self.draws if injected else None,
                              store_history=s['store_history'],
-                             svl_obs_model=(s['svl_obs_index'] == 'model'))
+                             svl_obs_model=(s['svl_obs_index'] == 'model'), store_states=states)
             self._cfg_key = None if injected else cfg_key
         else:  # same data and geometry: only the parameters and the random stream change
-            engine.update_params(theta, seed=s['seed'], eval_ids=[eval_id])
+            engine.update_params(theta, seed=seed, eval_ids=[eval_id])
         engine.execute()
         out = engine.fetch()
         try:
@@ -166,11 +189,16 @@ class ParticleMethodsB200(object):
             w = np.exp(lw - lw.max(axis=1, keepdims=True))
             self.weights = (w / w.sum(axis=1, keepdims=True)).T.copy()
             self.ancestors = hist['ancestors'][0].T.astype(np.float64)
+        if self._have_rows:
             traj = out['traj'][0].reshape(1, T1).copy()  # particles[a_T[k], :] (Q9)
         else:
-            # without the (T+1, N) history the reference's row-of-the-storage-matrix trajectory
-            # (Q9) does not exist; the filtered mean is returned in its place
-            traj = filt.reshape(1, T1).copy()
+            # without all generations of the particles the reference's row-of-the-storage-matrix
+            # trajectory (Q9) does not exist: NaN, never a different estimator in its place
+            traj = np.full((1, T1), np.nan)
+            if not getattr(self, '_warned_rows', False):
+                warnings.warn("state_trajectory is NaN: the particle history ((T+1) x N x 8 bytes) exceeds "
+                              "STATE_HISTORY_BUDGET; set settings['store_states']=True to keep it anyway")
+                self._warned_rows = True
         self.results.update({'filt_state_est': filt,
                              'log_like': float(out['log_like'][0]),
                              'state_trajectory': traj,
@@ -190,9 +218,11 @@ class ParticleMethodsB200(object):
         self.name = "Bootstrap particle filter and fixed-lag particle smoother (B200)."
         no_obs = model.no_obs + 1
         no_params = model.no_params
-        if self.settings['fixed_lag'] < 1:
-            raise NameError("fixed_lag must be >= 1 for the smoother (standard.py:161 reads "
-                            "next_ancestor, which is undefined for fixed_lag=0)")
+        if self.settings['fixed_lag'] < 1 and self.settings['estimate_gradient']:
+            # the reference only trips over fixed_lag=0 inside its gradient branch (standard.py:160-163);
+            # without gradients it smooths with zero hops (smo == filt), and so does the device
+            raise NameError("name 'next_ancestor' is not defined (fixed_lag must be >= 1 when "
+                            "estimate_gradient is set, standard.py:161)")
         engine, out = self._evaluate(model, do_smoother=True)
         self._store_filter_results(model, engine, out)
         G = out['grad_terms'][0]  # (P, T+1), the reference's smo_gradient_est

@@ -16,7 +16,7 @@ class OracleEngine(object):
 
     def configure(self, obs, theta, no_particles, fixed_lag=0, do_smoother=True,
                   generate_initial_state=True, initial_state=0.0, resampling="systematic", seed=0,
-                  eval_ids=None, draws=None, store_history=False, svl_obs_model=False):
+                  eval_ids=None, draws=None, store_history=False, svl_obs_model=False, store_states=False):
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
         B = theta.shape[0]
         self._cfg = dict(obs=np.asarray(obs, dtype=np.float64).reshape(-1), theta=theta, N=int(no_particles),

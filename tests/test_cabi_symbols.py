@@ -59,3 +59,22 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pf_oracle" not in text and "import oracle" not in text, f
+
+
+def test_integration_doc_quotes_the_executed_binding():
+    """INTEGRATION.md section 2 shows examples/flps_binding.py verbatim (the GPU tier executes that file)."""
+    snippet = open(os.path.join(ROOT, "examples", "flps_binding.py")).read()
+    body = snippet.split("# --- snippet begin\n")[1].split("# --- snippet end")[0]
+    assert body.strip() in open(os.path.join(ROOT, "INTEGRATION.md")).read()
+
+
+def test_product_defaults_to_the_cuda_engine():
+    """The `engine=` / `engine_factory=` seams exist for the CPU test tier only: left alone, both classes
+    construct the CUDA engine (and fail loudly without a device) -- never an oracle-backed one."""
+    import inspect
+    from qnmh_sysid2018_b200 import batch, particle_methods
+    src = inspect.getsource(particle_methods.ParticleMethodsB200._get_engine)
+    assert "from .engine import Engine" in src and "oracle" not in src
+    src = inspect.getsource(batch.BatchedParticleFilter.__init__)
+    assert "from .engine import Engine" in src and "oracle" not in src
+    assert particle_methods.ParticleMethodsB200()._engine is None

@@ -1,0 +1,312 @@
+"""GPU parity tests at BASELINE.json's own configurations and kernel instantiations (round-2 gaps):
+
+  (a) C2 geometry: N = 2^20, default launch geometry (148 cooperating CTAs, ITEMS = 7), both the
+      production flavour (Philox, replayed through the oracle) and the general flavour (injected noise)
+  (b) C3 instantiation: batch of N = 4096 filters, one CTA each, ITEMS = 9, shared-memory ancestor ring
+  (c) C4 shape: SV and SV-leverage at N = 2^16
+  (d) filter-only launches (do_smoother = 0; the bpf_* half of the boundary, alg_type 'mh0')
+  (e) the binding INTEGRATION.md documents (examples/flps_binding.py -> pfb200_run)
+  (f) the model-consistent leverage index (PFB200_FLAG_SVL_OBS_MODEL)
+  (g) fp32 against the fp64 oracle on injected noise: the documented fp32 bound
+  (h) the distributed filter's peer paths on ONE GPU (two rank handles in this process)
+
+All through the C ABI; the oracle is the checker.  Large-N cases use the step-locked comparison of
+tests/stepwise.py (ancestors bit exact away from verified CDF ties, which are counted and printed)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import stepwise as sw
+from oracle import pf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+THETA = {"lgss": np.array([0.2, 0.5, 1.0, 0.5]), "sv": np.array([0.5, 0.95, 0.25]),
+         "sv_leverage": np.array([0.5, 0.95, 0.25, -0.3])}
+
+
+def _engine(kind, dtype="float64", **opts):
+    from qnmh_sysid2018_b200.engine import Engine
+    eng = Engine(kind, dtype, 0)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    return eng
+
+
+def _obs(kind, T, seed):
+    rng = np.random.default_rng(seed)
+    th = THETA[kind]
+    x, obs = th[0], np.zeros(T + 1)
+    for t in range(1, T + 1):
+        x = th[0] + th[1] * (x - th[0]) + th[2] * rng.standard_normal()
+        obs[t] = x + th[3] * rng.standard_normal() if kind == "lgss" else np.exp(0.5 * x) * rng.standard_normal()
+    return obs
+
+
+def _first(d):
+    return {k: v[0] for k, v in d.items()}
+
+
+# ---------------------------------------------------------------------------------------------- (a)
+@pytest.mark.parametrize("flavour", ["production_philox", "general_injected"])
+def test_c2_geometry_matches_oracle(flavour):
+    """The instantiation bench.py times -- pf_persistent_kernel<LGSS, double, 512, 7, 1, GENERAL=0> on 148
+    cooperating CTAs -- and its general twin, at N = 2^20."""
+    N, T, L, seed, ev = 1 << 20, 24, 10, 87655678, 4
+    obs = _obs("lgss", T, 1)
+    eng = _engine("lgss")
+    if flavour == "production_philox":
+        draws = sw.philox_draws(eng, seed, ev, N, T)
+        out = eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=[ev],
+                      store_history=True)
+    else:
+        draws = orc.random_draws(np.random.default_rng(3), N, T)
+        out = eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", draws=draws, store_history=True)
+    assert eng.info("ctas_per_filter") == 148 and eng.info("items") == 7 and eng.info("cooperative") == 1
+    ties = sw.check_history(orc.MODEL_LGSS, THETA["lgss"], obs, _first(eng.fetch_history()),
+                            _first(eng.fetch_steps()), _first(out), draws, L)
+    print("C2 %s: %d verified CDF-tie mismatches in %d particle-steps" % (flavour, ties, N * T))
+    # ring mode (what the bench runs) gives the same numbers as history mode
+    if flavour == "production_philox":
+        ring = eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=[ev])
+        for k in ("log_like", "filt", "smo", "grad_terms", "traj_index"):
+            np.testing.assert_array_equal(ring[k], out[k])
+
+
+# ---------------------------------------------------------------------------------------------- (b)
+def test_c3_instantiation_matches_oracle():
+    """Batch of one-CTA filters with ITEMS = 9 and the uint16 shared-memory ancestor ring, Philox noise
+    replayed through the oracle (free running: at N = 4096 a CDF tie has probability ~1e-9 per step)."""
+    B, N, T, L, seed = 12, 4096, 50, 10, 99
+    obs = _obs("lgss", T, 2)
+    rng = np.random.default_rng(5)
+    thetas = THETA["lgss"] + 0.03 * rng.standard_normal((B, 4))
+    evals = np.arange(100, 100 + B)
+    eng = _engine("lgss")
+    out = eng.run(obs, thetas, N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=evals, store_states=True)
+    assert eng.info("items") == 9 and eng.info("anc_smem") == 1 and eng.info("ctas_per_filter") == 1
+    for b in range(B):
+        draws = sw.philox_draws(eng, seed, int(evals[b]), N, T)
+        ref = orc.smoother(orc.MODEL_LGSS, thetas[b], obs, N, L, draws)
+        assert abs(out["log_like"][b] - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+        np.testing.assert_allclose(out["filt"][b], ref["filt_state_est"].reshape(-1), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out["smo"][b], ref["smo_state_est"].reshape(-1), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out["grad_terms"][b], ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
+        assert int(out["traj_index"][b]) == ref["trajectory_index"]
+        # PFB200_FLAG_STORE_STATES: the reference's row of the particle matrix without the full history
+        np.testing.assert_array_equal(out["traj"][b], ref["state_trajectory"].reshape(-1))
+    # the plain ring mode (the benchmarked launch) gives the same numbers
+    ring = eng.run(obs, thetas, N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=evals)
+    assert eng.info("items") == 9 and eng.info("anc_smem") == 1
+    for k in ("log_like", "filt", "smo", "grad_terms", "traj_index"):
+        np.testing.assert_array_equal(ring[k], out[k])
+    assert np.all(np.isnan(ring["traj"]))
+
+
+# ---------------------------------------------------------------------------------------------- (c)
+@pytest.mark.parametrize("kind", ["sv", "sv_leverage"])
+def test_c4_shape_matches_oracle(kind):
+    N, T, L, seed, ev = 1 << 16, 30, 10, 12, 7
+    obs = _obs(kind, T, 4)
+    eng = _engine(kind)
+    draws = sw.philox_draws(eng, seed, ev, N, T)
+    out = eng.run(obs, THETA[kind], N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=[ev], store_history=True)
+    ties = sw.check_history(gu.MODEL_IDS[kind], THETA[kind], obs, _first(eng.fetch_history()),
+                            _first(eng.fetch_steps()), _first(out), draws, L, exact_particles=(kind == "sv"),
+                            lw_rtol=1e-12)
+    print("C4 %s: G = %d CTAs, %d verified tie mismatches" % (kind, eng.info("ctas_per_filter"), ties))
+    ring = eng.run(obs, THETA[kind], N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=[ev])
+    for k in ("log_like", "filt", "smo", "grad_terms", "traj_index"):
+        np.testing.assert_array_equal(ring[k], out[k])
+
+
+# ---------------------------------------------------------------------------------------------- (d)
+@pytest.mark.parametrize("name", ["lgss_N1000_T500_L10", "sv_N256_T100_L5", "lgss_N2000_T120_L10"])
+def test_filter_only_launch_matches_golden_and_oracle(name):
+    """do_smoother = 0 (bpf_*): log-likelihood, filtered means and the trajectory draw of the reference's
+    golden run; no smoother output."""
+    g = gu.load(name)
+    eng = _engine(g["model_kind"])
+    draws = gu.draws_for(g)
+    out = eng.run(g["obs"], g["theta"], g["no_particles"], g["fixed_lag"], False, g["generate_initial_state"],
+                  g["initial_state"], g["resampling_method"], draws=draws, store_history=True)
+    ref = orc.particle_filter(g["model_id"], g["theta"], g["obs"], g["no_particles"], draws,
+                              initial_state_value=g["initial_state"],
+                              generate_initial_state=g["generate_initial_state"], resampling=g["resampling_method"])
+    hist = eng.fetch_history()
+    np.testing.assert_array_equal(hist["ancestors"][0], ref["ancestors"])
+    assert gu.sha(hist["ancestors"][0].astype(np.int32)) == str(g["ancestors_sha256"])
+    assert abs(out["log_like"][0] - g["log_like"]) <= 1e-10 * abs(g["log_like"])
+    np.testing.assert_allclose(out["filt"][0], g["filt_state_est"], rtol=1e-10, atol=1e-12)
+    assert int(out["traj_index"][0]) == ref["trajectory_index"]
+    np.testing.assert_allclose(out["traj"][0], g["state_trajectory"], rtol=1e-12, atol=1e-13)
+    assert not out["smo"].any() and not out["grad_terms"].any()
+    # ring mode, Philox: a filter-only launch equals the filter part of a filter + smoother launch
+    a = eng.run(g["obs"], g["theta"], 20000, 10, False, True, 0.0, "systematic", seed=3, eval_ids=[1])
+    b = eng.run(g["obs"], g["theta"], 20000, 10, True, True, 0.0, "systematic", seed=3, eval_ids=[1])
+    for k in ("log_like", "filt", "traj_index"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_dropin_filter_method_matches_reference_golden():
+    """`ParticleMethodsB200.filter(model)` (what alg_type='mh0' calls, metropolis_hastings.py:328-329)."""
+    from qnmh_sysid2018_b200 import ParticleMethodsB200
+    from qnmh_sysid2018_b200.models import MODEL_CLASSES
+    g = gu.load("lgss_N500_T250_L10")
+    model = MODEL_CLASSES["lgss"]()
+    for k, v in zip(g["param_names"], g["theta"]):
+        model.params[k] = float(v)
+    model.set_observations(g["obs"])
+    model.fix_true_params()
+    model.create_inference_model(tuple(g["params_to_estimate"]))
+    pf = ParticleMethodsB200({"no_particles": g["no_particles"], "generate_initial_state": True, "rng": "injected"})
+    pf.draws = gu.draws_for(g)
+    pf.filter(model)
+    r = pf.results
+    assert abs(r["log_like"] - g["log_like"]) <= 1e-10 * abs(g["log_like"])
+    np.testing.assert_allclose(r["filt_state_est"].reshape(-1), g["filt_state_est"], rtol=1e-10, atol=1e-12)
+    # default settings keep the particle rows ('store_states': 'auto'): the reference's state_trajectory
+    np.testing.assert_array_equal(r["state_trajectory"].reshape(-1), g["state_trajectory"])
+    assert r["state_trajectory"].shape == (1, g["T"] + 1)
+    assert "smo_state_est" not in r
+    # fixed_lag = 0 without gradients smooths with zero hops (standard.py:146-157): smo == filt
+    pf0 = ParticleMethodsB200({"no_particles": g["no_particles"], "generate_initial_state": True,
+                               "rng": "injected", "fixed_lag": 0})
+    pf0.draws = gu.draws_for(g)
+    pf0.smoother(model)
+    np.testing.assert_allclose(pf0.results["smo_state_est"][1:], pf0.results["filt_state_est"][1:], rtol=1e-12, atol=1e-13)
+    assert not pf0.results["smo_gradient_est"].any()
+    pf0.settings["estimate_gradient"] = True
+    with pytest.raises(NameError):
+        pf0.smoother(model)
+
+
+# ---------------------------------------------------------------------------------------------- (e)
+def test_integration_binding_runs_pfb200_run():
+    """Executes examples/flps_binding.py -- the snippet of INTEGRATION.md section 2 -- and checks both
+    calls (`flps_lgss` -> pfb200_run(do_smoother=1), `bpf_lgss` -> do_smoother=0) against the oracle."""
+    spec = importlib.util.spec_from_file_location("flps_binding", os.path.join(ROOT, "examples", "flps_binding.py"))
+    fb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fb)
+    N, T, L, seed = 1000, 120, 10, 87655678
+    obs = _obs("lgss", T, 9)
+    mu, phi, sv, se = THETA["lgss"]
+    filt, smo, ll, grad, traj = fb.flps_lgss(obs, mu, phi, sv, se, no_particles=N, fixed_lag=L, seed=seed)  # eval_id 0
+    filt_b, ll_b, traj_b = fb.bpf_lgss(obs, mu, phi, sv, se, no_particles=N, seed=seed)                     # eval_id 1
+    eng = _engine("lgss")
+    ref = orc.smoother(orc.MODEL_LGSS, THETA["lgss"], obs, N, L, sw.philox_draws(eng, seed, 0, N, T))
+    assert abs(ll - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    np.testing.assert_allclose(filt, ref["filt_state_est"].reshape(-1), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(smo, ref["smo_state_est"].reshape(-1), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(grad.reshape(4, T + 1), ref["smo_gradient_est"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(traj, ref["state_trajectory"].reshape(-1))
+    ref_b = orc.particle_filter(orc.MODEL_LGSS, THETA["lgss"], obs, N, sw.philox_draws(eng, seed, 1, N, T))
+    assert abs(ll_b - ref_b["log_like"]) <= 1e-10 * abs(ref_b["log_like"])
+    np.testing.assert_allclose(filt_b, ref_b["filt_state_est"].reshape(-1), rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(traj_b, ref_b["state_trajectory"].reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------- (f)
+@pytest.mark.parametrize("N,G", [(3000, 1), (40000, 0)])
+def test_svl_model_consistent_obs_index(N, G):
+    """PFB200_FLAG_SVL_OBS_MODEL: the leverage term reads obs[t-1] (Cython twin / model definition,
+    cython_sv_leverage_helper.pyx:254) instead of obs[t] (NumPy twin)."""
+    T, L = 40, 6
+    obs = _obs("sv_leverage", T, 6)
+    draws = orc.random_draws(np.random.default_rng(N), N, T)
+    eng = _engine("sv_leverage", ctas_per_filter=G) if G else _engine("sv_leverage")
+    out = eng.run(obs, THETA["sv_leverage"], N, L, True, True, 0.0, "systematic", draws=draws, store_history=True,
+                  svl_obs_model=True)
+    sw.check_history(orc.MODEL_SVL, THETA["sv_leverage"], obs, _first(eng.fetch_history()), _first(eng.fetch_steps()),
+                     _first(out), draws, L, exact_particles=False, obs_index="model", lw_rtol=1e-12)
+    other = eng.run(obs, THETA["sv_leverage"], N, L, True, True, 0.0, "systematic", draws=draws)
+    assert abs(other["log_like"][0] - out["log_like"][0]) > 1e-6  # the switch does something
+    # and through the drop-in estimator's setting
+    from qnmh_sysid2018_b200 import ParticleMethodsB200
+    from qnmh_sysid2018_b200.models import MODEL_CLASSES
+    model = MODEL_CLASSES["sv_leverage"]()
+    for k, v in zip(model.params.keys(), THETA["sv_leverage"]):
+        model.params[k] = float(v)
+    model.set_observations(obs)
+    model.fix_true_params()
+    model.create_inference_model(("mu", "phi", "sigma_v", "rho"))
+    pf = ParticleMethodsB200({"no_particles": N, "fixed_lag": L, "generate_initial_state": True, "rng": "injected",
+                              "svl_obs_index": "model", "estimate_gradient": True})
+    pf.draws = draws
+    pf.smoother(model)
+    assert pf.results["log_like"] == float(out["log_like"][0])
+
+
+# ---------------------------------------------------------------------------------------------- (g)
+FP32_BOUND = {"anc_rate_per_N": 2.0 ** -20, "ll_rel": 2e-4, "score_rel": 5e-2, "smo_abs": 5e-3}
+
+
+@pytest.mark.parametrize("N", [1 << 14, 1 << 18])
+def test_fp32_documented_bound_on_injected_noise(N):
+    """fp32 storage / per-particle arithmetic (CDF, reductions, outputs stay fp64) against the fp64 oracle
+    on the SAME injected noise.  Documented bound, asserted here:
+      * step-locked ancestor mismatch rate  <= N * 2^-20 per particle-step (the fp32 `exp` of the shifted
+        log-weight is good to ~2^-22 relative, so a position within that distance of a CDF step may pick
+        the neighbouring parent),
+      * free-running log-likelihood: relative error <= 2e-4,
+      * free-running score (sum of the score terms): error <= 5 % of its norm + 0.05,
+      * smoothed means: absolute error <= 5e-3."""
+    T, L = 30, 10
+    obs = _obs("lgss", T, 8)
+    draws = orc.random_draws(np.random.default_rng(N + 1), N, T)
+    eng = _engine("lgss", "float32")
+    out = eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", draws=draws, store_history=True)
+    hist = _first(eng.fetch_history())
+    x, lw, anc = hist["particles"], hist["log_weights"], hist["ancestors"]
+    w, _, _ = sw.normalised_weights(lw)
+    mism = 0
+    for t in range(1, T + 1):
+        a_ref = orc.systematic(w[t - 1], draws.u[t])
+        d = anc[t] != a_ref
+        mism += int(d.sum())
+        assert np.abs(anc[t][d] - a_ref[d]).max(initial=0) <= 3  # only ever a neighbouring parent
+        x_ref = orc.generate_state(orc.MODEL_LGSS, THETA["lgss"], obs, x[t - 1][anc[t]], t, draws.z[t])
+        np.testing.assert_allclose(x[t], x_ref, rtol=4e-7, atol=4e-7)
+    rate = mism / float(N * T)
+    ref = orc.smoother(orc.MODEL_LGSS, THETA["lgss"], obs, N, L, draws)
+    ll_rel = abs(out["log_like"][0] - ref["log_like"]) / abs(ref["log_like"])
+    s32, s64 = out["grad_terms"][0].sum(axis=1), ref["smo_gradient_est"].sum(axis=1)
+    score_err = np.abs(s32 - s64).max()
+    smo_err = np.abs(out["smo"][0] - ref["smo_state_est"].reshape(-1)).max()
+    print("fp32 N=%d: ancestor mismatch rate %.3e (bound %.3e), ll rel err %.2e, score err %.3e (|score| %.3e), smo err %.2e"
+          % (N, rate, N * FP32_BOUND["anc_rate_per_N"], ll_rel, score_err, np.abs(s64).max(), smo_err))
+    assert rate <= N * FP32_BOUND["anc_rate_per_N"]
+    assert ll_rel <= FP32_BOUND["ll_rel"]
+    assert score_err <= FP32_BOUND["score_rel"] * np.linalg.norm(s64) + 0.05
+    assert smo_err <= FP32_BOUND["smo_abs"]
+
+
+# ---------------------------------------------------------------------------------------------- (h)
+@pytest.mark.parametrize("N,T,L,gl,resampling", [(1 << 20, 12, 4, 74, "systematic"), (100001, 20, 3, 16, "systematic"),
+                                                 (200000, 16, 5, 32, "stratified"), (60000, 12, 4, 8, "multinomial")])
+def test_sharded_filter_two_ranks_on_one_gpu(N, T, L, gl, resampling):
+    """The distributed filter's code paths (peer stores of children, halo mirrors, system-scope
+    all-gathers, peer lineage walks) with both ranks on THIS GPU: 2 x gl CTAs must reproduce the
+    single-handle run with 2 * gl CTAs bit for bit (same CDF tiling, Philox keyed by global index)."""
+    from qnmh_sysid2018_b200.distributed import LocalShardedParticleFilter
+    obs = _obs("lgss", T, N % 97)
+    sh = LocalShardedParticleFilter("lgss", "float64", devices=(0, 0), ctas_per_rank=gl)
+    d = sh.run(obs, THETA["lgss"], N, L, seed=11, eval_id=3, resampling=resampling)
+    one_eng = _engine("lgss", ctas_per_filter=2 * gl)
+    one = one_eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, resampling, seed=11, eval_ids=[3])
+    assert one_eng.info("ctas_per_filter") == 2 * gl
+    assert d["log_like_per_rank"][0] == d["log_like_per_rank"][1] == one["log_like"][0]
+    np.testing.assert_allclose(d["filt"][0], one["filt"][0], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(d["smo"][0], one["smo"][0], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(d["grad_terms"][0], one["grad_terms"][0], rtol=1e-10, atol=1e-11)
+    assert int(d["traj_index"][0]) == int(one["traj_index"][0])  # trajectory draw across ranks
+    # a second evaluation re-uses the connection (update_params only) and still matches a fresh run
+    th2 = THETA["lgss"] * np.array([1.1, 0.9, 1.05, 1.0])
+    d2 = sh.run(obs, th2, N, L, seed=11, eval_id=4, resampling=resampling)
+    one2 = one_eng.run(obs, th2, N, L, True, True, 0.0, resampling, seed=11, eval_ids=[4])
+    assert d2["log_like_per_rank"][0] == one2["log_like"][0]
+    np.testing.assert_allclose(d2["grad_terms"][0], one2["grad_terms"][0], rtol=1e-10, atol=1e-11)
+    sh.close()
