@@ -241,47 +241,72 @@ def test_svl_model_consistent_obs_index(N, G):
 
 
 # ---------------------------------------------------------------------------------------------- (g)
-FP32_BOUND = {"anc_rate_per_N": 2.0 ** -20, "ll_rel": 2e-4, "score_rel": 5e-2, "smo_abs": 5e-3}
+# The documented fp32 bound.  fp32 = storage and per-particle arithmetic (rings,
+# normals, propagate, log-weight, exp of the shifted weight); CDF, reductions and outputs stay fp64.
+FP32_BOUND = {
+    "particle_rel": 4e-7,          # step-locked: x_t against the fp64 propagate of the same parent and noise
+    "logw_abs": 1e-6,              # step-locked: log-weight, relative to 1 + |logw|
+    "anc_rate_per_N": 2.0 ** -28,  # step-locked: ancestor mismatch rate per particle-step, times 1/N
+    "ll_term_abs": 5e-7,           # step-locked: log-likelihood term against fp64 on the stored fp32 log-weights
+    "filt_abs": 2e-7,              # step-locked: filtered mean, likewise
+    "smo_rel": 1e-7,               # smoother on the device genealogy: smoothed means / score terms, fp64 replay
+    "ll_rel_free": 5e-4,           # free running against the fp64 oracle on the same noise (the two filters
+                                   # decouple at the first ancestor that differs: a Monte Carlo difference)
+}
 
 
 @pytest.mark.parametrize("N", [1 << 14, 1 << 18])
 def test_fp32_documented_bound_on_injected_noise(N):
-    """fp32 storage / per-particle arithmetic (CDF, reductions, outputs stay fp64) against the fp64 oracle
-    on the SAME injected noise.  Documented bound, asserted here:
-      * step-locked ancestor mismatch rate  <= N * 2^-20 per particle-step (the fp32 `exp` of the shifted
-        log-weight is good to ~2^-22 relative, so a position within that distance of a CDF step may pick
-        the neighbouring parent),
-      * free-running log-likelihood: relative error <= 2e-4,
-      * free-running score (sum of the score terms): error <= 5 % of its norm + 0.05,
-      * smoothed means: absolute error <= 5e-3."""
+    """fp32 against the fp64 oracle on the SAME injected noise, step-locked (every time step from the
+    generation the device stored), plus the free-running log-likelihood / score difference (printed)."""
     T, L = 30, 10
+    th = THETA["lgss"]
     obs = _obs("lgss", T, 8)
     draws = orc.random_draws(np.random.default_rng(N + 1), N, T)
     eng = _engine("lgss", "float32")
-    out = eng.run(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", draws=draws, store_history=True)
-    hist = _first(eng.fetch_history())
+    out = _first(eng.run(obs, th, N, L, True, True, 0.0, "systematic", draws=draws, store_history=True))
+    hist, steps = _first(eng.fetch_history()), _first(eng.fetch_steps())
     x, lw, anc = hist["particles"], hist["log_weights"], hist["ancestors"]
-    w, _, _ = sw.normalised_weights(lw)
-    mism = 0
+    w, m, S = sw.normalised_weights(lw)
+    mism, worst = 0, dict(x=0.0, lw=0.0)
     for t in range(1, T + 1):
         a_ref = orc.systematic(w[t - 1], draws.u[t])
         d = anc[t] != a_ref
         mism += int(d.sum())
-        assert np.abs(anc[t][d] - a_ref[d]).max(initial=0) <= 3  # only ever a neighbouring parent
-        x_ref = orc.generate_state(orc.MODEL_LGSS, THETA["lgss"], obs, x[t - 1][anc[t]], t, draws.z[t])
-        np.testing.assert_allclose(x[t], x_ref, rtol=4e-7, atol=4e-7)
+        if d.any():  # a differing ancestor is a near-tie: the position sits within 2^-20 of the CDF steps skipped
+            cdf = np.cumsum(w[t - 1])
+            for n in np.flatnonzero(d):
+                lo, hi = sorted((int(anc[t][n]), int(a_ref[n])))
+                assert np.abs(cdf[lo:hi] - (n + draws.u[t]) / N).max() <= 2.0 ** -20
+        x_ref = orc.generate_state(orc.MODEL_LGSS, th, obs, x[t - 1][anc[t]], t, draws.z[t])
+        worst["x"] = max(worst["x"], float((np.abs(x[t] - x_ref) / (1.0 + np.abs(x_ref))).max()))
+        lw_ref = orc.evaluate_obs(orc.MODEL_LGSS, th, obs, x[t], t)
+        worst["lw"] = max(worst["lw"], float((np.abs(lw[t] - lw_ref) / (1.0 + np.abs(lw_ref))).max()))
     rate = mism / float(N * T)
-    ref = orc.smoother(orc.MODEL_LGSS, THETA["lgss"], obs, N, L, draws)
-    ll_rel = abs(out["log_like"][0] - ref["log_like"]) / abs(ref["log_like"])
-    s32, s64 = out["grad_terms"][0].sum(axis=1), ref["smo_gradient_est"].sum(axis=1)
-    score_err = np.abs(s32 - s64).max()
-    smo_err = np.abs(out["smo"][0] - ref["smo_state_est"].reshape(-1)).max()
-    print("fp32 N=%d: ancestor mismatch rate %.3e (bound %.3e), ll rel err %.2e, score err %.3e (|score| %.3e), smo err %.2e"
-          % (N, rate, N * FP32_BOUND["anc_rate_per_N"], ll_rel, score_err, np.abs(s64).max(), smo_err))
+    ll_ref = m + np.log(S) - np.log(N)
+    ll_ref[0] = 0.0
+    ll_err = float(np.abs(steps["ll_terms"] - ll_ref).max())
+    filt_ref = (w * x).sum(axis=1)
+    filt_ref[0] = 0.0
+    filt_err = float(np.abs(out["filt"] - filt_ref).max())
+    sm = orc.fixed_lag_smoother(orc.MODEL_LGSS, th, obs, dict(particles=x, weights=w, ancestors=anc,
+                                                               filt_state_est=filt_ref.reshape(-1, 1)), L)
+    smo_err = float(np.abs(out["smo"] - sm["smo_state_est"].reshape(-1)).max())
+    g_scale = np.abs(sm["smo_gradient_est"]).max()
+    grad_err = float(np.abs(out["grad_terms"] - sm["smo_gradient_est"]).max() / g_scale)
+    ref = orc.smoother(orc.MODEL_LGSS, th, obs, N, L, draws)
+    ll_rel = abs(out["log_like"] - ref["log_like"]) / abs(ref["log_like"])
+    s32, s64 = out["grad_terms"].sum(axis=1), ref["smo_gradient_est"].sum(axis=1)
+    print("fp32 N=%d step-locked: particle rel %.2e, logw %.2e, ancestor mismatch rate %.3e (= N * %.3e), ll term %.2e, "
+          "filt %.2e, smo %.2e, score terms %.2e | free running: ll rel %.2e, score %s vs fp64 %s, smo abs %.2e"
+          % (N, worst["x"], worst["lw"], rate, rate / N, ll_err, filt_err, smo_err, grad_err, ll_rel,
+             np.round(s32, 3), np.round(s64, 3), np.abs(out["smo"] - ref["smo_state_est"].reshape(-1)).max()))
+    assert worst["x"] <= FP32_BOUND["particle_rel"] and worst["lw"] <= FP32_BOUND["logw_abs"]
     assert rate <= N * FP32_BOUND["anc_rate_per_N"]
-    assert ll_rel <= FP32_BOUND["ll_rel"]
-    assert score_err <= FP32_BOUND["score_rel"] * np.linalg.norm(s64) + 0.05
-    assert smo_err <= FP32_BOUND["smo_abs"]
+    assert ll_err <= FP32_BOUND["ll_term_abs"] and filt_err <= FP32_BOUND["filt_abs"]
+    assert smo_err <= FP32_BOUND["smo_rel"] and grad_err <= FP32_BOUND["smo_rel"]
+    assert ll_rel <= FP32_BOUND["ll_rel_free"]
+    assert np.all(np.isfinite(s32))
 
 
 # ---------------------------------------------------------------------------------------------- (h)
