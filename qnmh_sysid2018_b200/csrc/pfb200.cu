@@ -17,10 +17,19 @@
 using namespace pfb200;
 
 typedef void (*KernelFn)(const pfb200::DeviceProblem);
-KernelFn pfb200_kernel_lgss(int dtype, bool general, int items);
-KernelFn pfb200_kernel_sv(int dtype, bool general, int items);
-KernelFn pfb200_kernel_svl(int dtype, bool general, int items);
-KernelFn pfb200_kernel_lgss_fa(int dtype, bool general, int items);
+// getters of the 16 instantiation objects (pf_instance.cu): pfb200_kernel_<model>_<dtype>_<general>(items)
+#define PFB_DECLARE_MODEL(m)                                                     \
+  KernelFn pfb200_kernel_##m##_0_0(int); KernelFn pfb200_kernel_##m##_0_1(int);   \
+  KernelFn pfb200_kernel_##m##_1_0(int); KernelFn pfb200_kernel_##m##_1_1(int);
+#define PFB_PICK_MODEL(m)                                                                        \
+  return dtype == 0 ? (general ? pfb200_kernel_##m##_0_1(items) : pfb200_kernel_##m##_0_0(items))  \
+                    : (general ? pfb200_kernel_##m##_1_1(items) : pfb200_kernel_##m##_1_0(items));
+PFB_DECLARE_MODEL(0)
+#ifndef PFB_LGSS_ONLY
+PFB_DECLARE_MODEL(1)
+PFB_DECLARE_MODEL(2)
+PFB_DECLARE_MODEL(3)
+#endif
 
 namespace {
 
@@ -80,15 +89,15 @@ constexpr int kItemsSmall = PFB_ITEMS_SMALL;  // small filters: a CTA's parent r
 constexpr int kChunk = kBlock * kItems;
 
 
-// The persistent kernel is instantiated per model in pf_instances_*.cu (separate translation units,
-// compiled in parallel); each exposes its four flavours through this getter.
+// The persistent kernel is instantiated in pf_instance.cu, compiled once per (model, dtype, flavour) into
+// separate objects (built in parallel).
 KernelFn kernel_for_model(int model, int dtype, bool general, int items) {
   switch (model) {
-    case kModelLGSS: return pfb200_kernel_lgss(dtype, general, items);
+    case kModelLGSS: PFB_PICK_MODEL(0)
 #ifndef PFB_LGSS_ONLY
-    case kModelSV: return pfb200_kernel_sv(dtype, general, items);
-    case kModelSVL: return pfb200_kernel_svl(dtype, general, items);
-    case kModelLGSSFA: return pfb200_kernel_lgss_fa(dtype, general, items);
+    case kModelSV: PFB_PICK_MODEL(1)
+    case kModelSVL: PFB_PICK_MODEL(2)
+    case kModelLGSSFA: PFB_PICK_MODEL(3)
 #endif
   }
   return nullptr;
@@ -314,6 +323,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "items")) *value = h->items;
   else if (!strcmp(name, "anc_smem")) *value = h->prob.anc_smem;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
+  else if (!strcmp(name, "win_cap")) *value = h->prob.win_cap;
   else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
   else if (!strcmp(name, "span")) *value = h->prob.span;
   else if (!strcmp(name, "l2_persist_max")) *value = (long long)h->l2_persist_max;
@@ -327,6 +337,18 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   } else return fail(PFB200_EINVAL, "pfb200_get_info: unknown key '%s'", name);
   return PFB200_OK;
 }
+
+// Children window of the expansion (systematic resampling): the children of a CDF tile are about as many
+// as its parents; the margin keeps the usual fluctuation inside ONE pass (more children: more passes).
+static int window_cap(int tile_cap) {
+  const int w = tile_cap + (tile_cap / 4 > 512 ? tile_cap / 4 : 512);
+  return (w + 3) & ~3;
+}
+#ifdef PFB_EXPAND
+static size_t window_bytes(int tile_cap) { return (size_t)(window_cap(tile_cap) + 4) * sizeof(int) + 8; }  // + alignment
+#else
+static size_t window_bytes(int) { return 16; }  // the expansion path is compiled out (see pf_kernels.cuh)
+#endif
 
 // seed + its Philox4x32 key schedule: key_r = key_0 + r * (0x9E3779B9, 0xBB67AE85)
 static void set_seed(DeviceProblem& p, uint64_t seed) {
@@ -406,7 +428,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     G = 1; G_loc = 1; per = N; tile_cap = chunk;
     for (int pass = 0; pass < 3; ++pass) {
       // shared memory of the current guess -> co-resident CTAs -> group size
-      smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
+      smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + window_bytes(tile_cap);
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
       if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
       capacity = bps * h->num_sms;
@@ -424,7 +446,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
       if (R == 1) { G = (N + per - 1) / per; G_loc = G; }  // no empty CTAs on a single GPU
       n_chunks = (per + chunk - 1) / chunk;
       const size_t want = (size_t)n_chunks * chunk;
-      tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : chunk;
+      tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) + window_bytes((int)want) <= smem_limit) ? (int)want : chunk;
     }
     const int alt_chunks = (per + kBlock * kItemsAlt - 1) / (kBlock * kItemsAlt);
     if (attempt == 0 && (h->opt_items == kItemsSmall || (h->opt_items == 0 && per <= kBlock * kItemsSmall))) items = kItemsSmall;
@@ -438,8 +460,12 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const int anc_stride = (N + 7) & ~7;
   const size_t anc_bytes = (size_t)RA_ring * anc_stride * sizeof(unsigned short);
   const bool anc_smem = h->opt_anc_smem && G == 1 && R == 1 && !history && do_smoother && N <= 65535 &&
-                        (size_t)(tile_cap + 1) * sizeof(double) + anc_bytes <= smem_limit;
-  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes : 0);
+                        (size_t)(tile_cap + 2) * sizeof(double) + anc_bytes <= smem_limit;
+  // children window of the expansion (systematic resampling): the children of a tile are about as many as
+  // its parents; the margin keeps the usual fluctuation inside ONE pass (more children: more passes)
+  const int win_cap = window_cap(tile_cap);
+  const size_t win_bytes = anc_smem ? 0 : window_bytes(tile_cap);
+  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes + 8 : win_bytes);
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
   capacity = bps * h->num_sms;
@@ -477,7 +503,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
+  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap; p.win_cap = win_cap;
   p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0; p.sjobs0 = 0;
   // distributed filter: ring rows are [halo | own span | halo] (mirrors of both neighbours' nearest
   // states and ancestors: lineage walks across a rank boundary stay in local memory)

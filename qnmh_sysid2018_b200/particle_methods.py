@@ -178,10 +178,10 @@ class ParticleMethodsB200(object):
             self.last_device_ms = None
         return engine, out
 
-    def _store_filter_results(self, model, engine, out):
+    def _store_filter_results(self, model, engine, out, b=0):
         T1 = model.no_obs + 1
-        filt = out['filt'][0].reshape(T1, 1).copy()
-        if self.settings['store_history']:
+        filt = out['filt'][b].reshape(T1, 1).copy()
+        if self.settings['store_history'] and engine is not None:
             hist = engine.fetch_history()
             # reference layout is particle-major (N, T+1) (standard.py:54-57)
             self.particles = hist['particles'][0].T.copy()
@@ -190,7 +190,7 @@ class ParticleMethodsB200(object):
             self.weights = (w / w.sum(axis=1, keepdims=True)).T.copy()
             self.ancestors = hist['ancestors'][0].T.astype(np.float64)
         if self._have_rows:
-            traj = out['traj'][0].reshape(1, T1).copy()  # particles[a_T[k], :] (Q9)
+            traj = out['traj'][b].reshape(1, T1).copy()  # particles[a_T[k], :] (Q9)
         else:
             # without all generations of the particles the reference's row-of-the-storage-matrix
             # trajectory (Q9) does not exist: NaN, never a different estimator in its place
@@ -200,9 +200,9 @@ class ParticleMethodsB200(object):
                               "STATE_HISTORY_BUDGET; set settings['store_states']=True to keep it anyway")
                 self._warned_rows = True
         self.results.update({'filt_state_est': filt,
-                             'log_like': float(out['log_like'][0]),
+                             'log_like': float(out['log_like'][b]),
                              'state_trajectory': traj,
-                             'trajectory_index': int(out['traj_index'][0])})
+                             'trajectory_index': int(out['traj_index'][b])})
         if self.settings['verbose']:
             print("Log-likelihood estimate is: " + str(self.results['log_like']))
 
@@ -225,7 +225,13 @@ class ParticleMethodsB200(object):
                             "estimate_gradient is set, standard.py:161)")
         engine, out = self._evaluate(model, do_smoother=True)
         self._store_filter_results(model, engine, out)
-        G = out['grad_terms'][0]  # (P, T+1), the reference's smo_gradient_est
+        self._store_smoother_results(model, out)
+
+    def _store_smoother_results(self, model, out, b=0):
+        """Host side of `smoother` for row b of a (possibly batched) device result."""
+        no_obs = model.no_obs + 1
+        no_params = model.no_params
+        G = out['grad_terms'][b]  # (P, T+1), the reference's smo_gradient_est
         grad_est = np.zeros(no_params)
         hess_est = np.zeros((no_params, no_params))
         if self.settings['estimate_gradient']:
@@ -237,7 +243,7 @@ class ParticleMethodsB200(object):
             if not np.all(np.isfinite(hess_est)):
                 print("Numerical problems in Segal-Weinstein estimator, returning identity.")
                 hess_est = np.eye(no_params)
-        self.results.update({'smo_state_est': out['smo'][0].reshape(no_obs, 1).copy(),
+        self.results.update({'smo_state_est': out['smo'][b].reshape(no_obs, 1).copy(),
                              'smo_gradient_est': G.copy(),
                              'log_joint_gradient_estimate': grad_est,
                              'log_joint_hessian_estimate': hess_est})

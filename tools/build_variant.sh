@@ -6,17 +6,8 @@ set -e
 NAME=$1; shift
 WHAT=${1:-lgss}; shift || true
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
-SRC=$ROOT/qnmh_sysid2018_b200/csrc
 OUT=$ROOT/build_variants/$NAME
 mkdir -p $OUT
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $*"
-if [ "$WHAT" = lgss ]; then UNITS="pfb200 pf_instances_lgss"; FLAGS="$FLAGS -DPFB_LGSS_ONLY"; else UNITS="pfb200 pf_instances_lgss pf_instances_sv pf_instances_svl pf_instances_lgss_fa"; fi
-pids=""
-for u in $UNITS; do
-  ( cd $SRC && nvcc $FLAGS -c -o $OUT/$u.o $u.cu 2> $OUT/$u.log ) &
-  pids="$pids $!"
-done
-for p in $pids; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libpfb200.so $(for u in $UNITS; do echo $OUT/$u.o; done)
-grep -h "error" $OUT/*.log || true
+if [ "$WHAT" = lgss ]; then MODELS="0"; else MODELS="0 1 2 3"; fi
+make -s -j8 -C $ROOT/qnmh_sysid2018_b200/csrc OUT=$OUT MODELS="$MODELS" EXTRA="$*" 2>&1 | grep -E "error|spill|registers" || true
 ls -la $OUT/libpfb200.so

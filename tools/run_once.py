@@ -47,8 +47,8 @@ print("N=%d T=%d B=%d %s G=%d groups=%d: kernel ms %s -> %.2f G particle-steps/s
          ["%.3f" % m for m in ms], units / min(ms) / 1e6, min(ms) * 1e3 / a.T, ll[0]))
 prof = eng.debug_profile()
 if prof.any():
-    names = ["A:scan(+rest)", "filt block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait", "xchg_max", "A:load+exp", "X1 arrive", "X2 arrive", "ch:search", "ch:gather", "ch:rng", "ch:model", "ch:store"]
+    names = ["A:scan(+rest)", "filt block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait", "xchg_max", "A:load+exp", "X1 arrive", "X2 arrive", "expand barrier", "expand pass", "-", "-", "-"]
     per_step = prof / float(a.T) / 1.965e3  # us at 1965 MHz
     for i, nm in enumerate(names):
         print("   %-20s mean %7.2f us  max %7.2f us  min %7.2f us" % (nm, per_step[:, i].mean(), per_step[:, i].max(), per_step[:, i].min()))
-    print("   total (mean over CTAs) %.2f us/step" % per_step[:, :11].sum(axis=1).mean())
+    print("   total (mean over CTAs) %.2f us/step" % per_step[:, :13].sum(axis=1).mean())
