@@ -34,9 +34,7 @@
 namespace pfb200 {
 
 #ifdef PFB_PROFILE
-// per-phase cycle counters kept in shared memory by thread 0 of the filter warps (no registers of the other
-// threads: the instrumented build keeps the register allocation of the real one)
-#define PFB_TICK(slot) do { if (tid == 0) { const long long now__ = clock64(); sh_prof[slot] += now__ - sh_prof[kProfSlots]; sh_prof[kProfSlots] = now__; } } while (0)
+#define PFB_TICK(slot) do { const long long now__ = clock64(); prof_acc[slot] += now__ - prof_t; prof_t = now__; } while (0)
 #else
 #define PFB_TICK(slot) do { } while (0)
 #endif
@@ -57,7 +55,6 @@ struct DeviceProblem {
   int R, rank, G_loc, span;
   unsigned epoch0;  // exchanges completed by earlier launches (peer counters are never reset)
   int tile_cap;  // shared-memory CDF tile capacity (entries, multiple of the sub-chunk size)
-  int win_cap;   // shared-memory ancestor window (children per expansion pass, multiple of 4)
   int RX, RA, RW;  // ring depths: particles, ancestors, log-weights
   int do_smoother, gen_init, resampling, svl_obs_model;
   int inject, inject_per_filter, obs_per_filter, ws_per_filter;
@@ -123,8 +120,6 @@ struct PfKernel {
   static_assert(kChase % kGather == 0, "the walk width is a multiple of the gather width");
   static constexpr int kRedK = kMaxParams + 2;
   static constexpr bool kFA = is_fully_adapted(MODEL);  // weights of generation t look ahead to y_{t+1}
-  static constexpr int kHeavyCap = 32;   // parents per expansion pass whose children the whole block writes
-  static constexpr int kHeavyMin = 24;   // ... from this many children on
 
   const DeviceProblem& p;
   double* sh_s;    // [tile_cap] CDF tile
@@ -132,9 +127,6 @@ struct PfKernel {
   double* sh_red;  // [kWarps][kRedK] + scratch
   double* sh_c;    // [kNumConsts]
   unsigned short* sh_anc;  // [RA][anc_stride] shared-memory ancestor ring (anc_smem mode)
-  int* sh_win;             // [win_cap + 4] ancestors of the children being generated (same bytes as sh_anc:
-                           //   a filter uses one or the other)
-  int* sh_heavy;           // [1 + 3 * kHeavyCap] parents with many children, filled by the whole block
   double* sh_sred;     // [kSmootherWarps][kMaxParams + 1] smoother reduction scratch
   unsigned* sh_flags;  // [0] sequence number of the last complete generation, [1] smoother jobs done (G == 1)
   const int tid, lane, warp, g_loc, q, g;  // g: CTA index inside the (possibly multi-GPU) group
@@ -147,14 +139,14 @@ struct PfKernel {
   bool aborted;
   int sx = 0, sw = 0, sa = 0;  // ring slots of the generation being written (t mod RX / RW / RA)
 #ifdef PFB_PROFILE
-  long long* sh_prof = nullptr;  // [kProfSlots + 1] (last entry: time of the previous tick)
+  long long prof_acc[kProfSlots] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = 0;
 #endif
 
   __device__ PfKernel(const DeviceProblem& prob, double* smem, double* red, double* cst, double* sred,
-                      unsigned* flags, int* heavy)
+                      unsigned* flags)
       : p(prob), sh_s(smem), sh_x(smem + prob.tile_cap), sh_red(red), sh_c(cst),
-        sh_anc(reinterpret_cast<unsigned short*>(smem + ((prob.tile_cap + (prob.G > 1 ? prob.G : 1) + 1) & ~1))),
-        sh_win(reinterpret_cast<int*>(smem + ((prob.tile_cap + (prob.G > 1 ? prob.G : 1) + 1) & ~1))), sh_heavy(heavy),  // 16-byte aligned
+        sh_anc(reinterpret_cast<unsigned short*>(smem + prob.tile_cap + (prob.G > 1 ? prob.G : 1))),
         sh_sred(sred), sh_flags(flags), tid(threadIdx.x),
         lane(threadIdx.x & 31), warp(threadIdx.x >> 5), g_loc(blockIdx.x % prob.G_loc),
         q(blockIdx.x / prob.G_loc), g(prob.rank * prob.G_loc + blockIdx.x % prob.G_loc),
@@ -775,18 +767,12 @@ struct PfKernel {
     }
   }
 
-  // ---- children [n_lo, n_hi): resample + propagate + weight (phase B).  A thread owns 4 consecutive
-  //      children.  SRC says where their ancestors come from:
-  //        kSearch  binary search in the normalised CDF tile (stratified; multinomial: global CDF)
-  //        kWindow  read from the shared-memory window (or, for a one-CTA filter, the uint16 ancestor ring
-  //                 row) the expansion filled (systematic resampling)
-  static constexpr int kSearch = 0, kWindow = 1;
-  template <int SRC>
-  __device__ __forceinline__ void children_chunk(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
+  // ---- children of the normalised CDF tile: resample + propagate + weight (phase B).  A thread
+  //      owns 4 consecutive children: one binary search, then short forward merges.
+  __device__ void children_chunk(const double* tile, const Real* x_prev, Real* x_new, Real* lw_new,
                                  int* anc_new, const double* inj_z_t, const double* inj_u_t, int t,
                                  double u, unsigned long long eval_id, double y_prop, double y_obs,
-                                 int c0, int len, int n_lo, int n_hi, bool remote, int owner, double& mx,
-                                 int w0 = 0) {
+                                 int c0, int len, int n_lo, int n_hi, bool remote, int owner, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
     int top = 1;
     while (top * 2 <= len) top *= 2;
@@ -795,15 +781,14 @@ struct PfKernel {
     unsigned short* anc_sh = sh_anc + (size_t)sa * p.anc_stride;  // generation-t row (anc_smem mode)
     double cst[kNumConsts];
     load_step_consts<MODEL>(smem_base(sh_c), cst);
-    const int cj = (SRC == kSearch) ? c0 : 0;  // what turns j[] into a global parent index
-    const Real* xp_row = opaque(x_prev + (SRC == kSearch ? c0 : 0));  // the expansion stores global indices
-    // Two lane mappings (kSearch).  "Shuffle": a warp takes 31 consecutive quads per pass (lanes 0..30) and
+    const Real* xp_row = opaque(x_prev + c0);
+    // Two lane mappings.  "Shuffle": a warp takes 31 consecutive quads per pass (lanes 0..30) and
     // lane 31 only searches the first child of the NEXT quad, so that every quad gets the upper end
     // of its search window from its right neighbour by one shuffle.  "Pair": 32 quads per warp, every
     // lane runs a second descent for the next quad's first child.  The shuffle mapping executes half
     // the probes; the pair mapping is compiled into the ITEMS = 9 flavour, whose typical range of
     // 4096 particles is exactly two passes of 512 quads (it would be three passes of 496).
-    constexpr bool shuffle_map = (ITEMS != PFB_ITEMS_ALT) && SRC == kSearch;
+    constexpr bool shuffle_map = (ITEMS != PFB_ITEMS_ALT);
     constexpr int kQuadsPerWarp = shuffle_map ? 31 : 32;
     for (int qb = q0 + warp * kQuadsPerWarp; qb < q1; qb += kWarps * kQuadsPerWarp) {  // warp-uniform
       const int qq = qb + lane;
@@ -811,17 +796,7 @@ struct PfKernel {
       const int nb = 4 * qq;
       const bool full = own && nb >= n_lo && nb + 3 < n_hi;
       int j[4];
-      if (SRC == kWindow) {  // filled by the expansion: the int window, or the uint16 ring row of a one-CTA filter
-        if (own) {
-          if (p.anc_smem) {
-            const ushort4 a4 = *reinterpret_cast<const ushort4*>(anc_sh + nb);
-            j[0] = a4.x; j[1] = a4.y; j[2] = a4.z; j[3] = a4.w;
-          } else {
-            const int4 a4 = *reinterpret_cast<const int4*>(sh_win + (nb - w0));
-            j[0] = a4.x; j[1] = a4.y; j[2] = a4.z; j[3] = a4.w;
-          }
-        }
-      } else if (GENERAL && p.resampling == 2) {
+      if (GENERAL && p.resampling == 2) {
         // multinomial: j = #{ k < N-1 : cdf[k] < u_n } (searchsorted side='left' with the last CDF
         // entry forced to 1 > u_n), four descents over the global CDF side by side
         const int top_g = 1 << (31 - __clz(max(p.N - 1, 1)));
@@ -861,12 +836,8 @@ struct PfKernel {
 #pragma unroll
         for (int e = 0; e < 3; ++e) j[1 + e] = min(li[e], len - 1);
       }
+      PFB_TICK(11);
       if (!own) continue;
-      if (SRC != kSearch && !full) {  // slots outside [n_lo, n_hi) were not written by this expansion
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (nb + e < n_lo || nb + e >= n_hi) j[e] = c0;
-      }
       Real xp[4];
       if (GENERAL && dist && p.resampling == 2) {
         // multinomial parents of a distributed filter live anywhere: own span / halos, or a peer's ring
@@ -891,155 +862,33 @@ struct PfKernel {
         } else {
           philox_normal_pair_keys<Real>(p.pkeys, eval_id, (uint32_t)t, (uint32_t)(2 * qq + h), z0, z1);
         }
+#ifdef PFB_PROFILE
+        if (z0 == (Real)123456.789) mx = 0.0;
+        PFB_TICK(13);
+#endif
         const Real xa = Ops::propagate(cst, xp[2 * h], z0, y_prop);
         const Real xb = Ops::propagate(cst, xp[2 * h + 1], z1, y_prop);
         const Real la = (kFA && y_obs != y_obs) ? (Real)0 : Ops::logweight(cst, xa, y_obs);
         const Real lb = (kFA && y_obs != y_obs) ? (Real)0 : Ops::logweight(cst, xb, y_obs);
         const int n = nb + 2 * h;
+#ifdef PFB_PROFILE
+        if (la == (Real)123456.789) mx = 0.0;
+        PFB_TICK(14);
+#endif
         if (full) {
           mx = dmax(mx, dmax((double)la, (double)lb));
           store2(x_new + n, xa, xb);
           store2(lw_new + n, la, lb);
-          const int ja = cj + j[2 * h], jb = cj + j[2 * h + 1];  // global parent indices
-          if (SRC == kWindow && p.anc_smem) { }  // the expansion wrote the ring row itself
-          else if (p.anc_smem) *reinterpret_cast<ushort2*>(anc_sh + n) = make_ushort2((unsigned short)ja, (unsigned short)jb);
-          else if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(ja, jb);
-          else st_hint_int2(anc_new + n, ja, jb, keep);
-          if (dist) { st_halo(owner, n, xa, ja); st_halo(owner, n + 1, xb, jb); }
+          if (p.anc_smem) *reinterpret_cast<ushort2*>(anc_sh + n) = make_ushort2((unsigned short)(c0 + j[2 * h]), (unsigned short)(c0 + j[2 * h + 1]));
+          else if (remote) *reinterpret_cast<int2*>(anc_new + n) = make_int2(c0 + j[2 * h], c0 + j[2 * h + 1]);
+          else st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
+          if (dist) { st_halo(owner, n, xa, c0 + j[2 * h]); st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         } else {
-          const int ja = cj + j[2 * h], jb = cj + j[2 * h + 1];
-          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (SRC == kWindow && p.anc_smem) { } else if (p.anc_smem) anc_sh[n] = (unsigned short)ja; else if (remote) anc_new[n] = ja; else st_hint_int(anc_new + n, ja, keep); if (dist) st_halo(owner, n, xa, ja); }
-          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (SRC == kWindow && p.anc_smem) { } else if (p.anc_smem) anc_sh[n + 1] = (unsigned short)jb; else if (remote) anc_new[n + 1] = jb; else st_hint_int(anc_new + n + 1, jb, keep); if (dist) st_halo(owner, n + 1, xb, jb); }
+          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); if (dist) st_halo(owner, n, xa, c0 + j[2 * h]); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); if (dist) st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         }
+        PFB_TICK(15);
       }
-    }
-  }
-
-
-  // ------------------------------------------------------------------------------------------
-  // Systematic resampling by EXPANSION (parent-centric).  pos(n) = (n + u) / N increases with n, so
-  // parent jl of a CDF tile owns the contiguous children [e(jl-1), e(jl)) with
-  //     e(jl) = #{ n : pos(n) < cdf[jl] }      (the first child whose position is not below cdf[jl]),
-  // the same assignment as the reference's a[n] = #{ j : cdf[j] <= pos(n) } (resampling.pyx:78-83):
-  // cdf[jl] <= pos(n)  <=>  n >= e(jl).  A thread evaluates e() for the parents of its scan run in
-  // closed form -- ceil(cdf N - u), corrected with the exactly rounded positions of the two
-  // candidates -- and writes the parent's index into its children's slots of a shared-memory window
-  // (or straight into the uint16 ancestor ring row of a one-CTA filter).  The children then READ
-  // their ancestor: no per-child binary search, no dependent shared-memory probe chain.
-  // ------------------------------------------------------------------------------------------
-  __device__ __forceinline__ double pos_of(double nd, double u) const {  // position() for a child index held as a double
-    const double a = __dadd_rn(nd, u);
-    return pow2N ? __dmul_rn(a, invN) : __ddiv_rn(a, (double)p.N);
-  }
-  // min{ n in [0, N] : NOT (pos(n) < c) }.  The estimate ceil(c N - u) is off by at most one: c N - u carries
-  // a rounding error of ~N 2^-52 << 1, so it and the exact answer can only differ when c N - u is that close
-  // to an integer, and then both lie in {k, k + 1}.
-  __device__ __forceinline__ int first_child_not_below(double c, double u) const {
-    // clamp in the integer domain (F2I saturates, NaN -> 0): NaN CDF (all weights zero) -> 0
-    const int n0 = min(max(__double2int_ru(fma(c, (double)p.N, -u)), 0), p.N);
-    const double nd = (double)n0;
-    const bool down = n0 > 0 && !(pos_of(nd - 1.0, u) < c);
-    const bool up = n0 < p.N && pos_of(nd, u) < c;
-    return n0 - (down ? 1 : 0) + (up ? 1 : 0);
-  }
-
-  // parents raw[0, lenc) of one scan sub-chunk (tile-local indices jl0 ...; raw = local inclusive sums, base =
-  // everything before the sub-chunk) -> slots [w0, w1) of the window / ring row.  The loops are deliberately
-  // NOT unrolled: one copy of the closed form (its exactly rounded division for N that is not a power of two
-  // is long), and a scatter loop that runs its 0-3 typical iterations instead of a 24-deep predicated cascade.
-  __device__ __forceinline__ void expand_subchunk(bool RING16, const double* raw, double base, double invS, double u, int c0, int jl0,
-                                                  int lenc, int last_jl, bool has_before, double c_before, int n_lo,
-                                                  int n_hi, int w0, int w1) {
-    const int first = tid * ITEMS;
-    if (first >= lenc) return;
-    unsigned short* row16 = sh_anc + (size_t)sa * p.anc_stride;
-    const int kend = min(ITEMS, lenc - first);
-    int e_prev = n_lo;
-#pragma unroll 1
-    for (int k = -1; k < kend; ++k) {
-      const int jl = first + k;
-      double cj = c_before;
-      if (jl >= 0) cj = __dmul_rn(__dadd_rn(base, raw[jl]), invS);
-      int e = n_lo;
-      if (jl >= 0 || has_before) e = min(max(first_child_not_below(cj, u), n_lo), n_hi);
-      if (jl0 + jl == last_jl) e = n_hi;
-      if (k >= 0) {
-        const int a = max(e_prev, w0), b = min(e, w1);
-        const int val = c0 + jl0 + jl;
-        bool queued = false;
-        if (b - a >= kHeavyMin) {
-          const int slot = atomicAdd(sh_heavy, 1);
-          if (slot < kHeavyCap) {
-            sh_heavy[1 + 3 * slot] = a; sh_heavy[2 + 3 * slot] = b; sh_heavy[3 + 3 * slot] = val;
-            queued = true;
-          }
-        }
-        if (!queued) {
-#pragma unroll 1
-          for (int n = a; n < b; ++n) {
-            if (RING16) row16[n] = (unsigned short)val;
-            else sh_win[n - w0] = val;
-          }
-        }
-      }
-      e_prev = e;
-    }
-  }
-
-  // children [n_lo, n_hi) of the parents [c0, c0 + own_len) whose RAW scan sub-chunks sit in `tile` (n_sub
-  // sub-chunks of kChunk entries, totals in sub_tot; base0 = group prefix before the first one)
-  __device__ __forceinline__ void children_systematic(const double* tile, int n_sub, int own_len, double base0, const double* sub_tot,
-                                      double invS, const Real* x_prev, Real* x_new, Real* lw_new, int* anc_new,
-                                      const double* inj_z_t, int t, double u, unsigned long long eval_id, double y_prop,
-                                      double y_obs, int c0, int n_lo, int n_hi, double& mx) {
-    if (n_hi <= n_lo) return;  // block-uniform
-    const bool ring16 = p.anc_smem != 0;
-    const int wcap = ring16 ? n_hi : p.win_cap;
-    for (int w0 = ring16 ? 0 : (n_lo & ~3); w0 < n_hi; w0 += wcap) {
-      const int w1 = ring16 ? n_hi : min(w0 + wcap, n_hi);
-      double base = base0, c_before = 0.0;
-      for (int c = 0; c < n_sub; ++c) {
-        const double* raw = tile + c * kChunk;
-        const int lenc = min(kChunk, own_len - c * kChunk);
-        expand_subchunk(ring16, raw, base, invS, u, c0, c * kChunk, lenc, own_len - 1, c > 0, c_before, n_lo, n_hi, w0, w1);
-        if (c + 1 < n_sub) {
-          c_before = __dmul_rn(__dadd_rn(base, raw[kChunk - 1]), invS);
-          base += sub_tot[c];
-        }
-      }
-      PFB_TICK(12);
-      fsync();
-      const int heavy = min(sh_heavy[0], kHeavyCap);  // block-uniform
-      if (heavy > 0) {
-        unsigned short* row16 = sh_anc + (size_t)sa * p.anc_stride;
-        for (int h = 0; h < heavy; ++h) {
-          const int a = sh_heavy[1 + 3 * h], b = sh_heavy[2 + 3 * h], val = sh_heavy[3 + 3 * h];
-          for (int n = a + tid; n < b; n += BLOCK) {
-            if (ring16) row16[n] = (unsigned short)val;
-            else sh_win[n - w0] = val;
-          }
-        }
-        fsync();
-        if (tid == 0) sh_heavy[0] = 0;
-      }
-      PFB_TICK(11);
-      const int wlo = max(n_lo, w0), whi = w1;
-      if (!dist) {
-        children_chunk<kWindow>(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, nullptr, t, u, eval_id, y_prop, y_obs, c0, own_len, wlo, whi, false, 0, mx, w0);
-      } else {
-        for (int r = wlo / p.span; r < p.R && r * p.span < whi; ++r) {
-          const int s_lo = max(wlo, r * p.span), s_hi = min(whi, (r + 1) * p.span);
-          if (r == p.rank) {
-            children_chunk<kWindow>(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, nullptr, t, u, eval_id, y_prop, y_obs, c0, own_len, s_lo, s_hi, false, r, mx, w0);
-          } else {  // global-index views of rank r's generation-t rows
-            Real* xv = peer_row(reinterpret_cast<Real*>(p.peer_x[r]), r, sx);
-            Real* lv = peer_row(reinterpret_cast<Real*>(p.peer_lw[r]), r, sw);
-            int* av = peer_row(p.peer_anc[r], r, sa);
-            children_chunk<kWindow>(tile, x_prev, xv, lv, av, inj_z_t, nullptr, t, u, eval_id, y_prop, y_obs, c0, own_len, s_lo, s_hi, true, r, mx, w0);
-          }
-        }
-      }
-      if (w1 < n_hi) fsync();  // the next pass overwrites the window
     }
   }
 
@@ -1050,8 +899,8 @@ struct PfKernel {
                                double u, unsigned long long eval_id, double y_prop, double y_obs,
                                int c0, int len, int n_lo, int n_hi, double& mx) {
     if (!dist) {
-      children_chunk<kSearch>(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
-                              y_obs, c0, len, n_lo, n_hi, false, 0, mx);
+      children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
+                     y_obs, c0, len, n_lo, n_hi, false, 0, mx);
       return;
     }
     if (n_hi <= n_lo) return;
@@ -1059,14 +908,14 @@ struct PfKernel {
     for (int r = n_lo / p.span; r < p.R && r * p.span < n_hi; ++r) {
       const int s_lo = max(n_lo, r * p.span), s_hi = min(n_hi, (r + 1) * p.span);
       if (r == p.rank) {
-        children_chunk<kSearch>(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
-                                y_obs, c0, len, s_lo, s_hi, false, r, mx);
+        children_chunk(tile, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop,
+                       y_obs, c0, len, s_lo, s_hi, false, r, mx);
       } else {  // global-index views of rank r's generation-t rows
         Real* xv = peer_row(reinterpret_cast<Real*>(p.peer_x[r]), r, sx);
         Real* lv = peer_row(reinterpret_cast<Real*>(p.peer_lw[r]), r, sw);
         int* av = peer_row(p.peer_anc[r], r, sa);
-        children_chunk<kSearch>(tile, x_prev, xv, lv, av, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs, c0,
-                                len, s_lo, s_hi, true, r, mx);
+        children_chunk(tile, x_prev, xv, lv, av, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs, c0,
+                       len, s_lo, s_hi, true, r, mx);
       }
     }
   }
@@ -1173,7 +1022,7 @@ struct PfKernel {
       }
 
 #ifdef PFB_PROFILE
-      if (tid == 0) sh_prof[kProfSlots] = clock64();
+      prof_t = clock64();
 #endif
       // ---------------- phase A
       double accF = 0.0, A = 0.0, chunk_total = 0.0;
@@ -1226,43 +1075,7 @@ struct PfKernel {
       PFB_TICK(3);
       double mx = -INFINITY;
       int traj_cnt = 0;
-      // Systematic resampling: per-child binary search in the CDF tile (default), or the parent-centric
-      // expansion (-DPFB_EXPAND; same ancestors, measured SLOWER on B200: 8.0 vs 4.7 us per C2 time step --
-      // ~65 instructions per parent for the exactly rounded closed form + scatter against ~28 per child for
-      // the shared-memory descent; kept as a tested alternative)
-#ifdef PFB_EXPAND
-      constexpr bool kExpand = true;
-#else
-      constexpr bool kExpand = false;
-#endif
-      const bool expand = kExpand && !final_step && (!GENERAL || p.resampling == 0);  // systematic: parent-centric expansion
-      if (expand) {
-        // The tile keeps its raw local sums: every parent normalises its own entry in registers.  A resident
-        // tile expands in one go; a streamed tile one recomputed sub-chunk at a time, each into the children
-        // [n_cursor, n_hi) its CDF range covers.  (ONE call site: the expansion is inlined once.)
-        int n_cursor = n_begin;
-        double base = Pg;
-        const int n_seg = resident ? 1 : n_chunks;
-        for (int seg = 0; seg < n_seg; ++seg) {
-          int c0 = j_begin, len = own, n_sub = n_chunks, n_hi = n_end;
-          if (!resident) {
-            c0 = j_begin + seg * kChunk;
-            len = min(kChunk, j_end - c0);
-            n_sub = 1;
-            fsync();
-            load_chunk(sh_s, lw_prev, x_prev, c0, len, m, nullptr, nullptr);
-            chunk_total = scan_chunk(sh_s);
-            if (seg + 1 < n_chunks) {
-              n_hi = lower_bound_child(__dmul_rn(base + chunk_total, invS), u, t, inj_u_t, eval_id);
-              n_hi = max(n_cursor, min(n_hi, n_end));
-            }
-          }
-          children_systematic(sh_s, n_sub, len, base, sh_red + 264, invS, x_prev, x_new, lw_new, anc_new, inj_z_t, t, u,
-                              eval_id, y_prop, y_obs, c0, n_cursor, n_hi, mx);
-          n_cursor = n_hi;
-          base += chunk_total;
-        }
-      } else if (resident) {
+      if (resident) {
         // normalise the whole tile: (group prefix + sub-chunk carry + local prefix) * (1/S)
         double base = Pg;
         for (int c = 0; c < n_chunks; ++c) {
@@ -1286,7 +1099,7 @@ struct PfKernel {
             double* cg = dist ? p.peer_cdf[r] : p.cdf_g + (size_t)ws * NS;
             for (int jl = tid; jl < own; jl += BLOCK) cg[j_begin + jl] = sh_s[jl];
           }
-        } else if (GENERAL || !kExpand) {  // stratified resampling
+        } else {
           children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
                        y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
         }
@@ -1320,7 +1133,7 @@ struct PfKernel {
                 if (jl < len) cg[c0 + jl] = sh_s[jl];
               }
             }
-          } else if (GENERAL || !kExpand) {
+          } else {
             const double next_base = base + chunk_total;
             int n_hi = n_end;
             if (c + 1 < n_chunks) {
@@ -1338,8 +1151,8 @@ struct PfKernel {
         // every CTA's part of the CDF is published; the children of this CTA's own index range
         // search all of it (resampling.pyx:33-42: unsorted uniforms, ancestors in any tile)
         exchange(0.0);
-        children_chunk<kSearch>(dist ? p.cdf_g : p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
-                                eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, p.rank, mx);
+        children_chunk(dist ? p.cdf_g : p.cdf_g + (size_t)ws * NS, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u,
+                       eval_id, y_prop, y_obs, 0, N, j_begin, j_end, false, p.rank, mx);
       }
       if (final_step) {
         const int cnt = block_sum_int(traj_cnt);
@@ -1384,20 +1197,12 @@ __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_k
   __shared__ double sh_c[kNumConsts];
   __shared__ double sh_sred[(PFB_SMOOTH_THREADS / 32) * (kMaxParams + 1)];
   __shared__ unsigned sh_flags[4];
-  __shared__ int sh_heavy[1 + 3 * PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL>::kHeavyCap];
   if (threadIdx.x == 0) {
     sh_flags[0] = 0u;
     sh_flags[1] = prob.sjobs0;
-    sh_heavy[0] = 0;
   }
   __syncthreads();
-  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c, sh_sred, sh_flags, sh_heavy);
-#ifdef PFB_PROFILE
-  __shared__ long long sh_prof[kProfSlots + 1];
-  if (threadIdx.x < kProfSlots + 1) sh_prof[threadIdx.x] = 0;
-  __syncthreads();
-  k.sh_prof = sh_prof;
-#endif
+  PfKernel<MODEL, Real, BLOCK, ITEMS, GENERAL> k(prob, pf_smem, sh_red, sh_c, sh_sred, sh_flags);
   if (threadIdx.x >= BLOCK) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     if (!prob.do_smoother) return;
@@ -1416,7 +1221,7 @@ __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_k
   }
 #ifdef PFB_PROFILE
   if (threadIdx.x == 0)
-    for (int i = 0; i < kProfSlots; ++i) prob.prof[(size_t)blockIdx.x * kProfSlots + i] = k.sh_prof[i];
+    for (int i = 0; i < kProfSlots; ++i) prob.prof[(size_t)blockIdx.x * kProfSlots + i] = k.prof_acc[i];
 #endif
 }
 

@@ -323,7 +323,6 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "items")) *value = h->items;
   else if (!strcmp(name, "anc_smem")) *value = h->prob.anc_smem;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
-  else if (!strcmp(name, "win_cap")) *value = h->prob.win_cap;
   else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
   else if (!strcmp(name, "span")) *value = h->prob.span;
   else if (!strcmp(name, "l2_persist_max")) *value = (long long)h->l2_persist_max;
@@ -337,18 +336,6 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   } else return fail(PFB200_EINVAL, "pfb200_get_info: unknown key '%s'", name);
   return PFB200_OK;
 }
-
-// Children window of the expansion (systematic resampling): the children of a CDF tile are about as many
-// as its parents; the margin keeps the usual fluctuation inside ONE pass (more children: more passes).
-static int window_cap(int tile_cap) {
-  const int w = tile_cap + (tile_cap / 4 > 512 ? tile_cap / 4 : 512);
-  return (w + 3) & ~3;
-}
-#ifdef PFB_EXPAND
-static size_t window_bytes(int tile_cap) { return (size_t)(window_cap(tile_cap) + 4) * sizeof(int) + 8; }  // + alignment
-#else
-static size_t window_bytes(int) { return 16; }  // the expansion path is compiled out (see pf_kernels.cuh)
-#endif
 
 // seed + its Philox4x32 key schedule: key_r = key_0 + r * (0x9E3779B9, 0xBB67AE85)
 static void set_seed(DeviceProblem& p, uint64_t seed) {
@@ -428,7 +415,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
     G = 1; G_loc = 1; per = N; tile_cap = chunk;
     for (int pass = 0; pass < 3; ++pass) {
       // shared memory of the current guess -> co-resident CTAs -> group size
-      smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + window_bytes(tile_cap);
+      smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double);
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
       if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
       capacity = bps * h->num_sms;
@@ -446,7 +433,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
       if (R == 1) { G = (N + per - 1) / per; G_loc = G; }  // no empty CTAs on a single GPU
       n_chunks = (per + chunk - 1) / chunk;
       const size_t want = (size_t)n_chunks * chunk;
-      tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) + window_bytes((int)want) <= smem_limit) ? (int)want : chunk;
+      tile_cap = (n_chunks <= 8 && (want + G) * sizeof(double) <= smem_limit) ? (int)want : chunk;
     }
     const int alt_chunks = (per + kBlock * kItemsAlt - 1) / (kBlock * kItemsAlt);
     if (attempt == 0 && (h->opt_items == kItemsSmall || (h->opt_items == 0 && per <= kBlock * kItemsSmall))) items = kItemsSmall;
@@ -461,11 +448,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   const size_t anc_bytes = (size_t)RA_ring * anc_stride * sizeof(unsigned short);
   const bool anc_smem = h->opt_anc_smem && G == 1 && R == 1 && !history && do_smoother && N <= 65535 &&
                         (size_t)(tile_cap + 2) * sizeof(double) + anc_bytes <= smem_limit;
-  // children window of the expansion (systematic resampling): the children of a tile are about as many as
-  // its parents; the margin keeps the usual fluctuation inside ONE pass (more children: more passes)
-  const int win_cap = window_cap(tile_cap);
-  const size_t win_bytes = anc_smem ? 0 : window_bytes(tile_cap);
-  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes + 8 : win_bytes);
+  smem = (size_t)(tile_cap + (G > 1 ? G : 1)) * sizeof(double) + (anc_smem ? anc_bytes + 8 : 0);
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, h->kernel, kThreads, smem));
   if (bps < 1) return fail(PFB200_ECUDA, "pfb200_configure: kernel does not fit on an SM (%zu B smem)", smem);
   capacity = bps * h->num_sms;
@@ -503,7 +486,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
 
   DeviceProblem& p = h->prob;
   p = DeviceProblem{};
-  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap; p.win_cap = win_cap;
+  p.N = N; p.NS = (N + 31) & ~31; p.T = T; p.L = L; p.P = P; p.B = B; p.G = G; p.n_groups = n_groups; p.per_cta = per; p.tile_cap = tile_cap;
   p.R = R; p.rank = R > 1 ? rank : 0; p.G_loc = G_loc; p.span = R > 1 ? G_loc * per : p.NS; p.epoch0 = 0; p.sjobs0 = 0;
   // distributed filter: ring rows are [halo | own span | halo] (mirrors of both neighbours' nearest
   // states and ancestors: lineage walks across a rank boundary stay in local memory)
