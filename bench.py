@@ -241,23 +241,17 @@ def workload_config(args, model, B, N, T):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def gpu_arm(args):
+def measure(workload, dtype_key, steps, warmup, ctx, particles_log2=0, sample_clocks=True):
+    """One workload on the ranks of this job: device-resident throughput (CUDA events, max over ranks),
+    kernel-only duration, and the end-to-end figure through the host-buffer call.  Returns a dict on
+    every rank (the reductions are collective)."""
     import torch
     import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     from qnmh_sysid2018_b200.engine import Engine
 
-    model, B, N, T = WORKLOADS[args.workload]
-    dtype = {"f64": "float64", "f32": "float32"}[args.dtype]
+    rank, world, local_rank, stream = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["stream"]
+    model, B, N, T = WORKLOADS[workload]
+    dtype = {"f64": "float64", "f32": "float32"}[dtype_key]
     theta0 = THETA_LGSS if model == "lgss" else THETA_SV
     obs = synthetic_obs(model, T)
     rs = np.random.RandomState(777)
@@ -268,18 +262,15 @@ def gpu_arm(args):
         thetas[:, 2:] = np.abs(thetas[:, 2:])
     eval_ids = np.arange(B, dtype=np.uint64) + np.uint64(rank * B)
     B_total = B
-    if args.workload == "c3" and world > 1:
+    if workload == "c3" and world > 1:
         # the 4096 evaluations are one fixed batch sharded over the ranks (strong scaling); the
         # Philox stream of an evaluation is keyed by its global index
         from qnmh_sysid2018_b200.batch import shard_range
         lo, hi = shard_range(B, rank, world)
         thetas, eval_ids, B = thetas[lo:hi], np.arange(lo, hi, dtype=np.uint64), hi - lo
-
-    stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the events share it
-    torch.cuda.set_stream(stream)
-    sharded = args.workload == "c5" and world > 1  # ONE filter over all ranks (strong scaling)
-    if args.particles_log2:
-        N = 1 << args.particles_log2
+    sharded = workload == "c5" and world > 1  # ONE filter over all ranks (strong scaling)
+    if particles_log2:
+        N = 1 << particles_log2
     if sharded:
         from qnmh_sysid2018_b200.distributed import DistributedParticleFilter
         dpf = DistributedParticleFilter(model, dtype, local_rank)
@@ -297,36 +288,39 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.execute()
     barrier()
-    try:
-        gpu_uuid = torch.cuda.get_device_properties(local_rank).uuid
-    except Exception:
-        gpu_uuid = None
-    sampler = ClockSampler(local_rank, gpu_uuid)
-    sampler.start()
+    sampler = None
+    if sample_clocks:
+        try:
+            gpu_uuid = torch.cuda.get_device_properties(local_rank).uuid
+        except Exception:
+            gpu_uuid = None
+        sampler = ClockSampler(local_rank, gpu_uuid)
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         eng.execute()
     ev1.record(stream)
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     kernel_ms.append(eng.last_kernel_ms())
-    clocks = sampler.summary()
+    clocks = sampler.summary() if sampler else None
     eng.synchronize()
     ll = eng.fetch_log_like()
 
     # kernel-only duration, averaged over a few separately timed launches
-    for _ in range(min(4, args.steps)):
+    for _ in range(min(4, steps)):
         eng.execute()
         kernel_ms.append(eng.last_kernel_ms())
     kernel_ms = float(np.mean(kernel_ms))
 
-    # ---- end to end through the host-buffer call
+    # ---- end to end through the host-buffer call: every step uploads its inputs from pinned host memory
+    # (observations, parameters, stream ids) and reads its results back
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     h_obs, h_theta, h_ev = pin(obs), pin(thetas), pin(eval_ids)
     P = eng.no_params
@@ -334,72 +328,132 @@ def gpu_arm(args):
             "grad_terms": pin(np.empty((B, P, T + 1))), "traj_index": pin(np.empty(B, dtype=np.int32)),
             "traj": np.empty((B, T + 1))}
 
-    def e2e_step():
-        if sharded:  # inputs are re-uploaded and the peer memory re-connected on every call
-            dpf.prepare(h_obs, theta0, N, FIXED_LAG, seed=SEED, eval_id=0)
+    def e2e_step(i):
+        if sharded:
+            # an MH iteration on a connected sharded filter: new parameters and stream id go up (the peer
+            # mappings and exchange counters stay alive), the per-rank partial results come back and are summed
+            dpf.prepare(h_obs, theta0, N, FIXED_LAG, seed=SEED, eval_id=i)
             dpf.execute()
             return dpf.fetch()
         eng.configure(h_obs, h_theta, N, FIXED_LAG, True, True, 0.0, "systematic", seed=SEED, eval_ids=h_ev)
         eng.execute()
         return eng.fetch(outs)
 
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+    for i in range(max(1, warmup // 2)):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(steps):
+        e2e_step(100 + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = h_obs.nbytes + B * 16 * 8 + h_ev.nbytes  # obs + derived per-filter constants + Philox stream ids
+    if sharded:
+        h2d = P * 8 + 16 * 8 + 8  # parameters, derived constants, stream id (the observations stay resident)
+    else:
+        h2d = h_obs.nbytes + B * 16 * 8 + h_ev.nbytes  # obs + derived per-filter constants + Philox stream ids
     d2h = B * 8 + 2 * B * (T + 1) * 8 + B * P * (T + 1) * 8 + B * 4
 
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(t[0]), float(t[1])
+    total_ms, e2e_s, kernel_ms = float(t[0]), float(t[1]), float(t[2])
 
-    fixed_job = sharded or (args.workload == "c3" and world > 1)
+    fixed_job = sharded or (workload == "c3" and world > 1)
     units_per_step = B_total * N * T if fixed_job else world * B * N * T
-    value = units_per_step * args.steps / (total_ms * 1e-3)
-    e2e_value = units_per_step * args.steps / e2e_s
+    bytes_unit = algorithmic_bytes_per_particle_step(dtype_key, FIXED_LAG)
+    peak, peak_src = measured_peak_gbs()
+    per_gpu_units = B * N * T / (world if sharded else 1)
+    achieved = bytes_unit * per_gpu_units / (kernel_ms * 1e-3) / 1e9
+    res = {"model": model, "B": B, "B_total": B_total, "N": N, "T": T, "fixed_job": fixed_job,
+           "value": units_per_step * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
+           "e2e_value": units_per_step * steps / e2e_s, "e2e_ms_per_step": e2e_s / steps * 1e3,
+           "h2d": int(h2d), "d2h": int(d2h), "kernel_ms": kernel_ms, "achieved": achieved, "peak": peak,
+           "peak_src": peak_src, "bytes_unit": bytes_unit, "per_gpu_units": per_gpu_units, "clocks": clocks,
+           "log_like": float(ll[0]), "launches": eng.info("kernel_launches_per_execute") * steps,
+           "geometry": {"ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
+                        "block_threads": eng.info("block_threads"), "filter_threads": eng.info("filter_threads"),
+                        "cooperative": eng.info("cooperative")}}
+    if sharded:
+        dpf.close()
+    else:
+        eng.close()
+    return res
+
+
+def traffic_entry(workload, dtype_key):
+    """DRAM bytes per launch of the persistent kernel from the committed ncu capture (NOT measured in this
+    run; null for workloads that were not captured)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(tpath) as fh:
+            data = json.load(fh)
+        key = "%s_%s" % (workload, dtype_key)
+        return data.get(key), data.get(key + "_source")
+    except Exception:
+        return None, None
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the events share it
+    torch.cuda.set_stream(stream)
+    ctx = {"rank": rank, "world": world, "local_rank": local_rank, "stream": stream}
+
+    m = measure(args.workload, args.dtype, args.steps, args.warmup, ctx, args.particles_log2)
+
+    # ---- multi-GPU runs also record the two workloads that EXCHANGE something (the default one is independent
+    # replicates): the C3 batch sharded over the ranks (strong scaling, one gather at the end) and ONE filter
+    # sharded over the ranks (C5: children pushed over NVLink, per-step all-gathers inside the kernel)
+    extra = {}
+    if world > 1 and args.workload == "c2" and not args.no_extra:
+        def brief(r):
+            return {"value": r["value"], "unit": "particle-timesteps/s", "ms_per_step": r["ms_per_step"],
+                    "e2e": r["e2e_value"], "e2e_ms_per_step": r["e2e_ms_per_step"], "kernel_ms": r["kernel_ms"],
+                    "roofline_frac_per_gpu": r["achieved"] / r["peak"], "scaling": "strong",
+                    "no_particles": r["N"], "no_obs": r["T"], "filters": r["B_total"], "log_like_sample": r["log_like"],
+                    "ctas_per_filter": r["geometry"]["ctas_per_filter"]}
+        extra["c3_strong"] = brief(measure("c3", args.dtype, 3, 3, ctx, sample_clocks=False))
+        for k in (24, 26):
+            extra["c5_2p%d" % k] = brief(measure("c5", args.dtype, 3, 3, ctx, particles_log2=k, sample_clocks=False))
 
     if rank == 0:
-        bytes_unit = algorithmic_bytes_per_particle_step(args.dtype, FIXED_LAG)
-        peak, peak_src = measured_peak_gbs()
-        per_gpu_units = B * N * T / (world if sharded else 1)
-        achieved = bytes_unit * per_gpu_units / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                with open(tpath) as fh:
-                    traffic = json.load(fh).get("%s_%s" % (args.workload, args.dtype))
-            except Exception:
-                traffic = None
-        cpu = run_cpu_baseline(model, B, N, T, procs=1) if world == 1 and not args.no_cpu else None
+        model, N, T = m["model"], m["N"], m["T"]
+        traffic, traffic_src = traffic_entry(args.workload, args.dtype)
+        cpu = run_cpu_baseline(model, m["B"], N, T, procs=1) if world == 1 and not args.no_cpu else None
         line = {
-            "metric": "particle-timesteps/sec (PF+fixed-lag smoother)", "value": value,
+            "metric": "particle-timesteps/sec (PF+fixed-lag smoother)", "value": m["value"],
             "unit": "particle-timesteps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if fixed_job else "weak",
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if m["fixed_job"] else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, model, B_total, N, T),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": eng.info("kernel_launches_per_execute") * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "pf_persistent_kernel", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_particle_step": bytes_unit,
-                         "algorithmic_bytes_per_launch": bytes_unit * per_gpu_units,
-                         "peak_source": peak_src},
-            "geometry": {"ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
-                         "block_threads": eng.info("block_threads"), "filter_threads": eng.info("filter_threads"),
-                         "cooperative": eng.info("cooperative")},
-            "log_like_sample": float(ll[0]),
+            "config": workload_config(args, model, m["B_total"], N, T),
+            "clocks": m["clocks"],
+            "e2e": {"value": m["e2e_value"], "unit": "particle-timesteps/s", "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["e2e_ms_per_step"]},
+            "gpu_launches": m["launches"],
+            "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": m["peak"], "unit": "GB/s",
+                         "frac": m["achieved"] / m["peak"], "traffic": traffic,
+                         "traffic_source": (traffic_src or "not captured for this workload") +
+                                           " -- ncu dram__bytes of one launch, copied from profiles/traffic.json, not measured in this run",
+                         "kernel": "pf_persistent_kernel", "kernel_ms": m["kernel_ms"],
+                         "algorithmic_bytes_per_particle_step": m["bytes_unit"],
+                         "algorithmic_bytes_per_launch": m["bytes_unit"] * m["per_gpu_units"],
+                         "peak_source": m["peak_src"]},
+            "geometry": m["geometry"],
+            "log_like_sample": m["log_like"],
         }
+        if extra:
+            line["extra"] = extra
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -417,6 +471,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="multi-GPU: skip the c3_strong / c5 records")
     ap.add_argument("--particles-log2", type=int, default=0, help="override N = 2^k (c5 sweep)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -75,6 +75,7 @@ class ParticleMH(object):
         self.d = len(model.get_free_params())
         self.base_cov = np.eye(self.d) * 0.05 ** 2 if base_cov is None else np.asarray(base_cov)
         self.memory = int(memory)
+        self.max_drift = 0.01  # qn_initial_hessian_scaling of the reference's examples
         self.rng = np.random.default_rng(seed)
         self.use_grad = alg in ("mh1", "qmh")
         if self.use_grad:
@@ -94,7 +95,7 @@ class ParticleMH(object):
             prior_grad = m.log_prior_gradient()
             grad = np.array(res['gradient_internal'], dtype=float)
             grad = grad + np.array([prior_grad[k] for k in m.params_to_estimate])
-        if not np.isfinite(target):
+        if not np.isfinite(target) or (grad is not None and not np.all(np.isfinite(grad))):
             return None
         return dict(free=np.array(free_params, dtype=float), params=m.get_params().copy(),
                     target=target, log_like=float(res['log_like']), grad=grad)
@@ -106,8 +107,18 @@ class ParticleMH(object):
             if H is not None:
                 cov = H
         cov = self.eps ** 2 * cov
-        mean = state['free'] + (0.5 * cov @ state['grad'] if self.use_grad else 0.0)
-        return mean, cov
+        if not np.all(np.isfinite(cov)) or np.linalg.cond(cov) > 1e10:
+            cov = self.eps ** 2 * self.base_cov  # a degenerate quasi-Newton estimate: fixed covariance
+        if self.use_grad:
+            # 'scaled_gradient' safeguard (quasi_newton/main.py:108-110): the drift is never longer than
+            # `max_drift`; a state-dependent proposal, evaluated the same way for the reverse move
+            drift = 0.5 * cov @ state['grad']
+            norm = float(np.linalg.norm(drift))
+            if norm > self.max_drift:
+                cov = cov * max(self.max_drift / norm, 1e-4)
+                drift = 0.5 * cov @ state['grad']
+            return state['free'] + drift, cov
+        return state['free'], cov
 
     def run(self, no_iters, initial_free_params, burn_in=0, verbose=False):
         cur = self._evaluate(initial_free_params)
