@@ -102,6 +102,10 @@ struct DeviceProblem {
   double* peer_xval[8];
   unsigned* peer_xcount[8];
   double* peer_cdf[8];  // multinomial resampling: every rank keeps a full copy [N] of the normalised CDF
+  int RS;             // depth of the shifted-weight ring of the cluster kernel (the persistent kernel: 3, compiled in)
+  // cluster kernel (pf_cluster.cuh): one filter per thread-block cluster of `cluster` CTAs, per_cta = 2^lg_per
+  // parents per CTA, ancestors in a distributed-shared-memory ring of RA_s generations
+  int cluster, lg_per, RA_s;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1058,8 +1062,11 @@ struct PfKernel {
       const bool pull = GENERAL && p.resampling == 2;  // multinomial: children pull from the global CDF
       if (!final_step && !pull) {
         int nb = 0;
-        if (lane == 0) nb = (g == 0) ? 0 : lower_bound_child(__dmul_rn(Pg, invS), u, t, inj_u_t, eval_id);
-        if (lane == 1) nb = last_cta ? N : lower_bound_child(__dmul_rn(Pg1, invS), u, t, inj_u_t, eval_id);
+        if (lane < 2) {  // the SAME code on both boundaries: two divergent copies would run one after the other
+          const bool fixed = lane == 0 ? (g == 0) : last_cta;
+          const int r = lower_bound_child(__dmul_rn(lane == 0 ? Pg : Pg1, invS), u, t, inj_u_t, eval_id);
+          nb = fixed ? (lane == 0 ? 0 : N) : r;
+        }
         n_begin = __shfl_sync(0xffffffffu, nb, 0);
         n_end = __shfl_sync(0xffffffffu, nb, 1);
       }

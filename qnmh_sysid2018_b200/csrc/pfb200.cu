@@ -13,6 +13,7 @@
 #include "pf_config.h"
 #define PFB_UTILITY_KERNELS
 #include "pf_kernels.cuh"
+#include "pf_cluster.cuh"
 
 using namespace pfb200;
 
@@ -20,7 +21,12 @@ typedef void (*KernelFn)(const pfb200::DeviceProblem);
 // getters of the 16 instantiation objects (pf_instance.cu): pfb200_kernel_<model>_<dtype>_<general>(items)
 #define PFB_DECLARE_MODEL(m)                                                     \
   KernelFn pfb200_kernel_##m##_0_0(int); KernelFn pfb200_kernel_##m##_0_1(int);   \
-  KernelFn pfb200_kernel_##m##_1_0(int); KernelFn pfb200_kernel_##m##_1_1(int);
+  KernelFn pfb200_kernel_##m##_1_0(int); KernelFn pfb200_kernel_##m##_1_1(int);   \
+  KernelFn pfb200_cluster_kernel_##m##_0_0(); KernelFn pfb200_cluster_kernel_##m##_0_1(); \
+  KernelFn pfb200_cluster_kernel_##m##_1_0(); KernelFn pfb200_cluster_kernel_##m##_1_1();
+#define PFB_PICK_CLUSTER(m)                                                                        \
+  return dtype == 0 ? (general ? pfb200_cluster_kernel_##m##_0_1() : pfb200_cluster_kernel_##m##_0_0())  \
+                    : (general ? pfb200_cluster_kernel_##m##_1_1() : pfb200_cluster_kernel_##m##_1_0());
 #define PFB_PICK_MODEL(m)                                                                        \
   return dtype == 0 ? (general ? pfb200_kernel_##m##_0_1(items) : pfb200_kernel_##m##_0_0(items))  \
                     : (general ? pfb200_kernel_##m##_1_1(items) : pfb200_kernel_##m##_1_0(items));
@@ -103,6 +109,18 @@ KernelFn kernel_for_model(int model, int dtype, bool general, int items) {
   return nullptr;
 }
 
+// the cluster kernel (pf_cluster.cuh) of a model; nullptr: the model has none (fully adapted filter)
+KernelFn cluster_kernel_for_model(int model, int dtype, bool general) {
+  switch (model) {
+    case kModelLGSS: PFB_PICK_CLUSTER(0)
+#ifndef PFB_LGSS_ONLY
+    case kModelSV: PFB_PICK_CLUSTER(1)
+    case kModelSVL: PFB_PICK_CLUSTER(2)
+#endif
+  }
+  return nullptr;
+}
+
 // Derived constants with the reference's own expressions (Python float arithmetic == C double):
 //   linear_gaussian_model.py:87-90,223-237; stochastic_volatility_model_leverage.py:103-108,227-252
 void host_consts(int model, const double* th, double* c) {
@@ -163,6 +181,9 @@ struct pfb200_handle {
   long long opt_spin_limit = 20000000LL;
   long long opt_l2_persist = 0;
   long long opt_anc_smem = 1;       // shared-memory ancestor ring for one-CTA filters
+  long long opt_cluster = 0;        // cluster kernel: 0 = automatic, -1 = never, 1..16 = CTAs per filter (power of two)
+  long long opt_cluster_per = 128;  // automatic choice: parents per CTA the cluster size aims at
+  int cluster = 0;                  // CTAs per cluster of the configured problem (0: persistent kernel)
   long long opt_items = 0;          // 0 = automatic tile granularity, else PFB_ITEMS / PFB_ITEMS_ALT   // pin the ancestor ring in L2 (access policy window)
   size_t l2_persist_max = 0, l2_window_max = 0;
   // distributed single filter (one process per GPU, peer memory over NVLink)
@@ -302,6 +323,14 @@ int pfb200_set_option(pfb200_handle* h, const char* name, long long value) {
     h->opt_items = value;
   }
   else if (!strcmp(name, "anc_smem")) h->opt_anc_smem = value;
+  else if (!strcmp(name, "cluster")) {
+    if (value < -1 || value > kClMaxCluster || (value > 0 && (value & (value - 1))))
+      return fail(PFB200_EINVAL, "pfb200_set_option: cluster must be -1 (never), 0 (automatic) or a power of two <= %d", kClMaxCluster);
+    h->opt_cluster = value;
+  } else if (!strcmp(name, "cluster_per")) {
+    if (value < 2 || value > kClMaxPer) return fail(PFB200_EINVAL, "pfb200_set_option: cluster_per must be 2..%d", kClMaxPer);
+    h->opt_cluster_per = value;
+  }
   else if (!strcmp(name, "dist_world")) {
     if (value < 1 || value > 8) return fail(PFB200_EINVAL, "pfb200_set_option: dist_world must be 1..8");
     h->opt_dist_world = value;
@@ -322,6 +351,7 @@ int pfb200_get_info(pfb200_handle* h, const char* name, long long* value) {
   else if (!strcmp(name, "chunk")) *value = kBlock * h->items;
   else if (!strcmp(name, "items")) *value = h->items;
   else if (!strcmp(name, "anc_smem")) *value = h->prob.anc_smem;
+  else if (!strcmp(name, "cluster")) *value = h->cluster;
   else if (!strcmp(name, "tile_cap")) *value = h->prob.tile_cap;
   else if (!strcmp(name, "ctas_per_rank")) *value = h->prob.G_loc;
   else if (!strcmp(name, "span")) *value = h->prob.span;
@@ -469,6 +499,67 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   h->smem_bytes = smem;
   h->n_ws = history ? B : n_groups;
 
+  // ---- small / medium filters: one thread-block cluster per filter (pf_cluster.cuh) instead of the
+  //      persistent kernel.  Systematic resampling on one GPU; C CTAs of cap = 2^lg parents each.
+  h->cluster = 0;
+  int cl_lg = 0, cl_RAs = 0;
+  const bool cl_auto_ok = h->opt_ctas_per_filter == 0 && h->opt_items == 0;  // explicit persistent-kernel geometry wins
+  if ((h->opt_cluster > 0 || (h->opt_cluster == 0 && cl_auto_ok)) && R == 1 && resampling == PFB200_RESAMPLE_SYSTEMATIC &&
+      N <= kClMaxCluster * kClMaxPer) {
+    KernelFn ck = cluster_kernel_for_model(h->model, h->dtype, general);
+    int C = 1;
+    if (h->opt_cluster > 0) C = (int)h->opt_cluster;
+    else {
+      while (C < kClMaxCluster && (long long)C * h->opt_cluster_per < N) C *= 2;
+      while (C > 1 && (long long)B * C > h->num_sms) C /= 2;  // a batch keeps every filter resident
+    }
+    bool ok = ck != nullptr && (h->opt_cluster > 0 || (long long)B * C <= h->num_sms);
+    int cap = 0, lgc = 0, RAs = (L < T ? L : T) + kClLag;
+    size_t csmem = 0;
+    while (ok) {
+      cap = 32; lgc = 5;
+      while ((long long)cap * C < N) { cap *= 2; ++lgc; }
+      csmem = h->dtype == PFB200_F64 ? ClLayout<double>(cap, RAs, C).bytes : ClLayout<float>(cap, RAs, C).bytes;
+      if (cap <= kClMaxPer && csmem <= smem_limit) break;
+      if (C == kClMaxCluster || h->opt_cluster > 0) ok = false;
+      else C *= 2;
+    }
+    int max_clusters = 0;
+    if (ok) {
+      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+      if (C > 8) CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(C * (B < h->num_sms ? B : h->num_sms)));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = csmem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)ck, &cfg) != cudaSuccess || max_clusters < 1) {
+        (void)cudaGetLastError();
+        ok = false;
+        if (h->opt_cluster > 0)
+          return fail(PFB200_ECUDA, "pfb200_configure: a cluster of %d CTAs with %zu B of shared memory cannot be scheduled", C, csmem);
+      }
+    } else if (h->opt_cluster > 0) {
+      return fail(PFB200_EINVAL, "pfb200_configure: cluster = %d does not fit this problem (N = %d, model %d)", C, N, h->model);
+    }
+    if (ok) {
+      h->cluster = C;
+      h->kernel = ck;
+      h->cooperative = false;
+      G = G_loc = C; per = cap; tile_cap = cap; cl_lg = lgc; cl_RAs = RAs;
+      n_groups = history ? B : (B < max_clusters ? B : max_clusters);
+      if (!history && h->opt_max_groups > 0 && n_groups > h->opt_max_groups) n_groups = (int)h->opt_max_groups;
+      h->smem_bytes = csmem;
+      h->n_ws = history ? B : n_groups;
+      h->items = kItemsSmall;
+    }
+  }
+
   // A connected distributed handle keeps its peer mappings (and the running exchange counters) as long
   // as the geometry the mappings were made for is unchanged: an MH iteration re-configures / updates
   // parameters without touching the IPC handles.  Any other change needs pfb200_dist_disconnect on every
@@ -493,6 +584,11 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.halo = R > 1 ? (p.span < (1 << 17) ? p.span : (1 << 17)) : 0;
   if (R > 1) p.NS = p.span + 2 * p.halo;
   p.RX = (history || states) ? T + 1 : L + 3;  // +1: the smoother job of lag time t-2 overlaps the writes of generation t
+  p.RS = 3;
+  if (h->cluster) {  // smoother jobs run up to kClLag time steps behind the filter warps
+    p.cluster = h->cluster; p.lg_per = cl_lg; p.RA_s = cl_RAs; p.RS = 8;
+    if (!(history || states)) p.RX = L + kClLag;
+  }
   p.xs_per_filter = states ? 1 : 0;
   p.RA = history ? T + 1 : L + 2;
   p.RW = history ? T + 1 : 3;
@@ -504,7 +600,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   p.inject_per_filter = (flags & PFB200_FLAG_INJECT_PER_FILTER) ? 1 : 0;
   p.obs_per_filter = (flags & PFB200_FLAG_OBS_PER_FILTER) ? 1 : 0;
   p.ws_per_filter = history ? 1 : 0;
-  p.anc_smem = anc_smem ? 1 : 0;
+  p.anc_smem = (anc_smem && !h->cluster) ? 1 : 0;
   p.anc_stride = anc_stride;
   p.initial_state = initial_state;
   set_seed(p, seed);
@@ -530,7 +626,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   CUDA_TRY(h->x_ring.reserve((size_t)(states ? B : h->n_ws) * p.RX * p.NS * real_sz));
   CUDA_TRY(h->logw.reserve((size_t)h->n_ws * p.RW * p.NS * real_sz));
   CUDA_TRY(h->anc.reserve((size_t)h->n_ws * p.RA * p.NS * 4));
-  if (do_smoother) CUDA_TRY(h->s_ring.reserve((size_t)h->n_ws * 3 * p.NS * real_sz));
+  if (do_smoother) CUDA_TRY(h->s_ring.reserve((size_t)h->n_ws * p.RS * p.NS * real_sz));
   if (resampling == PFB200_RESAMPLE_MULTINOMIAL)  // distributed: every rank keeps a copy of the WHOLE CDF
     CUDA_TRY(h->cdf_g.reserve(R > 1 ? ((size_t)N + 32) * 8 : (size_t)h->n_ws * p.NS * 8));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
@@ -639,7 +735,20 @@ int pfb200_execute(pfb200_handle* h) {
     CUDA_TRY(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   }
   CUDA_TRY(cudaEventRecord(h->evk0, h->stream));
-  if (h->cooperative && !h->dist_same_device) {
+  if (h->cluster) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)h->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, h->kernel, p));
+  } else if (h->cooperative && !h->dist_same_device) {
     void* args[] = {&p};
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)h->kernel, grid, block, args, h->smem_bytes, h->stream));
   } else {

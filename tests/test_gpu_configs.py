@@ -85,7 +85,8 @@ def test_c3_instantiation_matches_oracle():
     rng = np.random.default_rng(5)
     thetas = THETA["lgss"] + 0.03 * rng.standard_normal((B, 4))
     evals = np.arange(100, 100 + B)
-    eng = _engine("lgss")
+    eng = _engine("lgss", cluster=-1)  # the persistent kernel's batched instantiation (a batch this small would
+                                       # otherwise go to the cluster kernel: tests/test_gpu_cluster.py)
     out = eng.run(obs, thetas, N, L, True, True, 0.0, "systematic", seed=seed, eval_ids=evals, store_states=True)
     assert eng.info("items") == 9 and eng.info("anc_smem") == 1 and eng.info("ctas_per_filter") == 1
     for b in range(B):

@@ -47,7 +47,8 @@ print("N=%d T=%d B=%d %s G=%d groups=%d: kernel ms %s -> %.2f G particle-steps/s
          ["%.3f" % m for m in ms], units / min(ms) / 1e6, min(ms) * 1e3 / a.T, ll[0]))
 prof = eng.debug_profile()
 if prof.any():
-    names = ["A:scan(+rest)", "filt block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait", "xchg_max", "A:load+exp", "X1 arrive", "X2 arrive", "expand barrier", "expand pass", "-", "-", "-"]
+    cl_names = ["children wait", "A: max/exp/scan", "s store + all-gather wait", "prefix + bounds", "normalise + publish", "B: search", "B: gather + normals", "B: propagate/weight/stores", "B: loop tail", "-", "-", "-", "-", "-", "-", "-"]
+    names = cl_names if eng.info("cluster") > 0 else ["A:scan(+rest)", "filt block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait", "xchg_max", "A:load+exp", "X1 arrive", "X2 arrive", "B: search", "-", "B: gather + normals", "B: propagate/weight", "B: stores"]
     per_step = prof / float(a.T) / 1.965e3  # us at 1965 MHz
     for i, nm in enumerate(names):
         print("   %-20s mean %7.2f us  max %7.2f us  min %7.2f us" % (nm, per_step[:, i].mean(), per_step[:, i].max(), per_step[:, i].min()))
