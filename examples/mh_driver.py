@@ -78,6 +78,7 @@ class ParticleMH(object):
         self.max_drift = 0.01  # qn_initial_hessian_scaling of the reference's examples
         self.rng = np.random.default_rng(seed)
         self.use_grad = alg in ("mh1", "qmh")
+        self.est_seconds, self.est_calls, self.est_device_ms = 0.0, 0, 0.0  # time spent in the state estimator
         if self.use_grad:
             estimator.settings['estimate_gradient'] = True  # metropolis_hastings.py:244-245
 
@@ -86,7 +87,11 @@ class ParticleMH(object):
         m.store_free_params(free_params)
         if not m.check_parameters():
             return None
+        t0 = time.perf_counter()
         (self.est.smoother if self.use_grad else self.est.filter)(m)
+        self.est_seconds += time.perf_counter() - t0
+        self.est_calls += 1
+        self.est_device_ms += getattr(self.est, 'last_device_ms', None) or 0.0
         res = self.est.results
         _, log_prior = m.log_prior()
         target = float(res['log_like']) + log_prior + m.log_jacobian()
@@ -104,7 +109,9 @@ class ParticleMH(object):
         cov = self.base_cov
         if self.alg == "qmh":
             H = damped_bfgs_inverse_hessian([h['free'] for h in hist], [h['grad'] for h in hist])
-            if H is not None:
+            # trust the quasi-Newton estimate only while it stays within a plausible scale (a proposal
+            # standard deviation of 1 in free-parameter space); otherwise keep the fixed covariance
+            if H is not None and np.max(np.linalg.eigvalsh(H)) <= 1.0:
                 cov = H
         cov = self.eps ** 2 * cov
         if not np.all(np.isfinite(cov)) or np.linalg.cond(cov) > 1e10:
@@ -154,4 +161,6 @@ class ParticleMH(object):
         return dict(params=chain, free_params=free_chain, log_like=ll, accepted=accepted,
                     accept_rate=float(accepted[1:].mean()), seconds=wall,
                     time_per_iteration=wall / max(1, no_iters - 1),
+                    estimator_calls=self.est_calls, estimator_seconds=self.est_seconds,
+                    estimator_device_ms_per_call=self.est_device_ms / max(1, self.est_calls),
                     posterior_mean=chain[burn_in:].mean(axis=0), posterior_std=chain[burn_in:].std(axis=0))

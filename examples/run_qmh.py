@@ -63,6 +63,9 @@ def main():
     print("model %s  alg %s  N=%d  T=%d  %d iterations: %.1f s (%.2f ms/iteration, %.2f G particle-steps/s)"
           % (a.model, a.alg, N, T, a.iters, out["seconds"], 1e3 * out["time_per_iteration"],
              N * T / out["time_per_iteration"] / 1e9))
+    print("state estimator: %d calls, %.2f ms per call on the host clock, %.2f ms per call on the device"
+          % (out["estimator_calls"], 1e3 * out["estimator_seconds"] / max(1, out["estimator_calls"]),
+             out["estimator_device_ms_per_call"]))
     print("accept rate %.2f; posterior mean %s, std %s; true %s"
           % (out["accept_rate"], np.round(out["posterior_mean"], 3), np.round(out["posterior_std"], 3),
              [model.true_params[k] for k in model.params_to_estimate]))
