@@ -348,6 +348,7 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
     int cpow = 1;
     while (cpow < C) cpow *= 2;
     const bool act = warp < n_act;
+    const bool bw = warp == (n_act < kWarps ? n_act : 0);  // the warp that computes the CTA's children range
     int* sh_bounds = reinterpret_cast<int*>(sh_red + 96);  // n_begin, n_end of the step (warp 0 -> everybody)
 
     fsync();
@@ -460,7 +461,7 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
       aborted = fsync_or(ab != 0);  // (1)
       if (aborted) return;
       publish_ring_rows(seq0 + (unsigned)tau);  // rows of generation tau were stored before this barrier
-      double mg = -INFINITY, A = 0.0, F = 0.0, pre0 = 0.0, pre1 = 0.0;
+      double mg = -INFINITY, A = 0.0, F = 0.0, pre0 = 0.0, pre1 = 0.0, woff = 0.0, winc = 0.0;
       double s[2] = {0.0, 0.0};
       if (act) {
         mg = (lane < kWarps) ? sh_red[lane] : -INFINITY;
@@ -489,7 +490,11 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
           if (lane >= o) wi += nb;
         }
         for (int o = npow >> 1; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
-        const double woff = __shfl_sync(0xffffffffu, wi - wt, warp);
+        // exclusive offset of this warp := inclusive prefix of the previous one (the SAME bits both warps use
+        // for their common boundary)
+        woff = __shfl_sync(0xffffffffu, wi, max(warp - 1, 0));
+        if (warp == 0) woff = 0.0;
+        winc = __shfl_sync(0xffffffffu, wi, warp);
         A = __shfl_sync(0xffffffffu, wi, npow - 1);
         F = __shfl_sync(0xffffffffu, fs, 0);
         pre0 += woff;
@@ -505,7 +510,7 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
       }
       // ---------------- all-gather complete: prefix over the cluster (every active warp on its own)
       ab = 0;
-      if (act) {
+      if (act || bw) {
         ab = warp_mbar_wait(sm0 + lay.bars + 8u * (xepoch & 1u), ((xepoch - 1u) >> 1) & 1u);
         PFB_TICK(2);
         double mr = -INFINITY, Ar = 0.0;
@@ -524,23 +529,26 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
           const double nb = __shfl_up_sync(0xffffffffu, vin, o);
           if (lane >= o) vin += nb;
         }
+        // exclusive prefix of CTA g := inclusive prefix of CTA g-1: neighbours agree bit for bit on their boundary
         const double Pg1 = __shfl_sync(0xffffffffu, vin, g);
-        const double Pg = __shfl_sync(0xffffffffu, vin - v, g);
+        double Pg = __shfl_sync(0xffffffffu, vin, max(g - 1, 0));
+        if (g == 0) Pg = 0.0;
         const double S = __shfl_sync(0xffffffffu, vin, C - 1);
         const double scale = __shfl_sync(0xffffffffu, sc, g);
         const double invS = 1.0 / S;
         // normalised CDF of the CTA's parents: (group prefix + rescaled local prefix) * (1/S)
-        if (j0 < own) this->sh_s[j0] = __dmul_rn(__dadd_rn(Pg, __dmul_rn(pre0, scale)), invS);
-        if (j0 + 1 < own) this->sh_s[j0 + 1] = __dmul_rn(__dadd_rn(Pg, __dmul_rn(pre1, scale)), invS);
+        const double c0 = __dmul_rn(__dadd_rn(Pg, __dmul_rn(pre0, scale)), invS);
+        const double c1 = __dmul_rn(__dadd_rn(Pg, __dmul_rn(pre1, scale)), invS);
+        if (j0 < own) this->sh_s[j0] = c0;
+        if (j0 + 1 < own) this->sh_s[j0 + 1] = c1;
+        if (bw && !final_step && lane < 2) {
+          // children range of this CTA: lanes 0 / 1 run the SAME code on the two boundaries.  The warp that
+          // does this holds no parents (when there is one): it runs beside the normalisation above.
+          const bool fixed = lane == 0 ? (g == 0) : last_cta;
+          const int nb = first_child_not_below(__dmul_rn(lane == 0 ? Pg : Pg1, invS), u);
+          sh_bounds[lane] = fixed ? (lane == 0 ? 0 : N) : nb;
+        }
         if (warp == 0) {
-          if (!final_step) {
-            // lanes 0 / 1 run the SAME code on the two boundaries (no serialised divergent copies)
-            if (lane < 2) {
-              const bool fixed = lane == 0 ? (g == 0) : last_cta;
-              const int nb = first_child_not_below(__dmul_rn(lane == 0 ? Pg : Pg1, invS), u);
-              sh_bounds[lane] = fixed ? (lane == 0 ? 0 : N) : nb;
-            }
-          }
           if (lane == 0) {
             p.filt_part[((size_t)b * (T + 1) + tau) * p.G_loc + g] = F * scale;
             *reinterpret_cast<double*>(reinterpret_cast<char*>(this->sh_s) + lay.wscale + 8u * ((uint32_t)tau & 7u)) = scale;
@@ -550,10 +558,12 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
             }
           }
           PFB_TICK(3);
-          // jobs whose ring slots phase B of this step overwrites: lag times <= t - kClLag
-          if (p.do_smoother && !final_step) ab |= wait_smoother_progress(min(max(t - kClLag - L + 1, 0), n_reg_jobs), 0u);
         }
       }
+      // jobs whose ring slots phase B of this step overwrites: lag times <= t - kClLag (checked by the last
+      // filter warp, off the critical path of the warps that hold parents whenever it holds none)
+      if (warp == kWarps - 1 && p.do_smoother && !final_step)
+        ab |= wait_smoother_progress(min(max(t - kClLag - L + 1, 0), n_reg_jobs), 0u);
       aborted = fsync_or(ab != 0);  // (3)
       if (aborted) return;
       // generation tau is complete (every CTA has passed its all-gather arrival) and this CTA's shifted
@@ -601,9 +611,9 @@ struct ClKernel : PfKernel<MODEL, Real, PFB_BLOCK, PFB_ITEMS_SMALL, GENERAL> {
         for (int pp = pp0 + tid; pp < pp1; pp += BLOCK) {
           const int n0 = 2 * pp;
           const bool v0 = n0 >= n_begin, v1 = n0 + 1 < n_end;
+          int ja, jb;
           const double pa = pos_sys(n0, u);
           const double pb = (n0 + 1 < N) ? pos_sys(n0 + 1, u) : INFINITY;
-          int ja, jb;
           search2(a_tile - 8u, pa, pb, own, top, ja, jb);
           ja = min(ja, own - 1);
           jb = min(jb, own - 1);
