@@ -370,7 +370,9 @@ def measure(workload, dtype_key, steps, warmup, ctx, particles_log2=0, sample_cl
            "h2d": int(h2d), "d2h": int(d2h), "kernel_ms": kernel_ms, "achieved": achieved, "peak": peak,
            "peak_src": peak_src, "bytes_unit": bytes_unit, "per_gpu_units": per_gpu_units, "clocks": clocks,
            "log_like": float(ll[0]), "launches": eng.info("kernel_launches_per_execute") * steps,
-           "geometry": {"ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
+           "geometry": {"kernel": "pf_cluster_kernel" if eng.info("cluster") > 0 else "pf_persistent_kernel",
+                        "cluster": eng.info("cluster"),
+                        "ctas_per_filter": eng.info("ctas_per_filter"), "groups": eng.info("n_groups"),
                         "block_threads": eng.info("block_threads"), "filter_threads": eng.info("filter_threads"),
                         "cooperative": eng.info("cooperative")}}
     if sharded:
@@ -445,7 +447,7 @@ def gpu_arm(args):
                          "frac": m["achieved"] / m["peak"], "traffic": traffic,
                          "traffic_source": (traffic_src or "not captured for this workload") +
                                            " -- ncu dram__bytes of one launch, copied from profiles/traffic.json, not measured in this run",
-                         "kernel": "pf_persistent_kernel", "kernel_ms": m["kernel_ms"],
+                         "kernel": m["geometry"]["kernel"], "kernel_ms": m["kernel_ms"],
                          "algorithmic_bytes_per_particle_step": m["bytes_unit"],
                          "algorithmic_bytes_per_launch": m["bytes_unit"] * m["per_gpu_units"],
                          "peak_source": m["peak_src"]},

@@ -5,7 +5,8 @@ import os
 import subprocess
 import sys
 
-tag, dtype = sys.argv[1], sys.argv[2]
+tag, dtype = sys.argv[1], sys.argv[2]  # files gpurun_out/<tag>_<dtype>_{launches.csv,full.ncu-rep,plain.json}
+wkey = sys.argv[3] if len(sys.argv) > 3 else "c2_%s" % dtype  # key in profiles/traffic.json
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = os.path.join(root, "gpurun_out")
 dst = os.path.join(root, "profiles")
@@ -56,8 +57,8 @@ traffic = to_bytes(*get("dram__bytes_read.sum")) + to_bytes(*get("dram__bytes_wr
 lines.append("  DRAM traffic per launch (read+write): %.3f GB" % (traffic / 1e9))
 tj = os.path.join(dst, "traffic.json")
 data = json.load(open(tj)) if os.path.exists(tj) else {}
-data["c2_%s" % dtype] = traffic
-data["c2_%s_source" % dtype] = "profiles/%s_%s_ncu_summary.txt" % (tag, dtype)
+data[wkey] = traffic
+data[wkey + "_source"] = "profiles/%s_%s_ncu_summary.txt" % (tag, dtype)
 json.dump(data, open(tj, "w"), indent=1)
 bench = open(os.path.join(src, "%s_%s_plain.json" % (tag, dtype))).read().strip()
 lines.append("== bench line of the same command (plain run, not under ncu)")
