@@ -100,7 +100,18 @@ int pfb200_set_stream(pfb200_handle* h, void* cuda_stream);
  *   "items"            parents per thread and scan sub-chunk: 7, 9 or 2 (0 = automatic)
  *   "anc_smem"         1 (default): filters of one CTA and N <= 65535 keep the ancestor ring in
  *                      shared memory; 0: always in global memory
- *   "dist_world", "dist_rank"  shard ONE filter over several GPUs (see pfb200_dist_* below) */
+ *   "cluster"          which kernel runs filters of up to 16 384 particles with systematic resampling on one
+ *                      GPU: 0 (default) = automatic -- the cluster kernel (one filter per thread-block
+ *                      cluster of C CTAs, parents / ancestors in distributed shared memory, one all-gather
+ *                      per time step; csrc/pf_cluster.cuh) whenever all B filters are resident at once
+ *                      (B * C <= SM count), else the persistent kernel; -1 = never; C = 1, 2, 4, 8, 16 =
+ *                      always, with C CTAs per filter (configure fails if the problem does not fit).  An
+ *                      explicit "ctas_per_filter" or "items" selects the persistent kernel.
+ *   "cluster_per"      parents per CTA the automatic cluster size aims at (default 128)
+ *   "dist_world", "dist_rank"  shard ONE filter over several GPUs (see pfb200_dist_* below)
+ * pfb200_get_info keys: "ctas_per_filter", "n_groups", "per_cta", "cluster" (CTAs per cluster, 0 = persistent
+ * kernel), "items", "anc_smem", "tile_cap", "smem_bytes", "cooperative", "block_threads", "filter_threads",
+ * "kernel_launches_per_execute", "workspace_bytes", "num_sms", ... */
 int pfb200_set_option(pfb200_handle* h, const char* name, long long value);
 int pfb200_get_info(pfb200_handle* h, const char* name, long long* value);
 
