@@ -40,14 +40,25 @@ enum ConstIdx {
 // ------------------------------------------------------------------------------------------
 enum PhiloxStream : unsigned { kStreamZ = 0u, kStreamU = 1u, kStreamUFinal = 2u };
 
+// hi:lo = a * M as ONE mul.wide.u32 (the C++ form `(uint64_t)M * a` reaches ptxas as a 64 x 64 multiply whose
+// zero high-word terms survive as additions of a zero uniform register: 2 dead instructions per round)
+__host__ __device__ __forceinline__ void philox_mulhilo(uint32_t m, uint32_t a, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(m));
+#else
+  const uint64_t p = (uint64_t)m * a;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+#endif
+}
+
 __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
-  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
-  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
-  const uint32_t n1 = (uint32_t)p1;
-  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
-  const uint32_t n3 = (uint32_t)p0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  uint32_t h0, l0, h1, l1;
+  philox_mulhilo(0xD2511F53u, c[0], h0, l0);
+  philox_mulhilo(0xCD9E8D57u, c[2], h1, l1);
+  const uint32_t n0 = h1 ^ c[1] ^ k0;
+  const uint32_t n2 = h0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
 }
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t eval_id, unsigned stream,
@@ -509,8 +520,25 @@ __device__ __forceinline__ float ld_hint(const float* p, uint64_t pol) {
   asm volatile("ld.relaxed.gpu.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
   return v;
 }
+// the same loads at a compile-time byte offset from one base pointer (address = register pair + immediate:
+// no per-load 64-bit address arithmetic)
+template <int OFF>
+__device__ __forceinline__ double ld_hint_off(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.f64 %0, [%1+%3], %2;" : "=d"(v) : "l"(p), "l"(pol), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float ld_hint_off(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.f32 %0, [%1+%3], %2;" : "=f"(v) : "l"(p), "l"(pol), "n"(OFF) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_hint_int2(int* p, int a, int b, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.s32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_int4(int* p, int a, int b, int c, int d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st_hint_int(int* p, int a, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(a), "l"(pol) : "memory");

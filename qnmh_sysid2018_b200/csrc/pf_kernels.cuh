@@ -194,6 +194,10 @@ struct PfKernel {
   // Independent work placed between arrive and wait overlaps the exchange latency and the skew.
   // `s_target` > 0: additionally wait until the smoother warps of every CTA of the group have
   // completed their first s_target jobs (their reads of the ring slots the next phase overwrites).
+  // MODE 0: sh_x[0..G) = the exchanged values (xchg_max / xchg_prefix reduce them in every warp).  MODE 1 / 2
+  // (groups of up to BLOCK CTAs): the warps that fetch the values scan / maximise their 32 in registers, so that
+  // after ONE more barrier a thread needs a handful of broadcast loads -- see fused_prefix / fused_max.
+  template <int MODE = 0>
   __device__ void exchange_wait(unsigned s_target = 0) {
     const int G = p.G;
     if (G == 1) {
@@ -212,8 +216,48 @@ struct PfKernel {
         ab = dist ? wait_counter<2>(cnt + 16, s_target * (unsigned)G) : wait_counter<1>(cnt + 16, s_target * (unsigned)G);
     }
     aborted = fsync_or(ab);  // block-uniform; orders the reads below after the acquire
-    for (int i = tid; i < G; i += BLOCK) sh_x[i] = ld_cg(val + i);
+    if (MODE != 0 && G <= BLOCK) {
+      if (tid < ((G + 31) & ~31)) {  // whole warps
+        if (MODE == 1) {
+          const double incl = warp_inclusive_scan(tid < G ? ld_cg(val + tid) : 0.0, lane);
+          sh_x[tid < G ? tid : G - 1] = incl;  // (idle lanes of the last warp repeat its total)
+          if (lane == 31) sh_red[kXw + warp] = incl;
+        } else {
+          double v = tid < G ? ld_cg(val + tid) : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0) sh_red[kXw + warp] = v;
+        }
+      }
+    } else {
+      for (int i = tid; i < G; i += BLOCK) sh_x[i] = ld_cg(val + i);
+    }
     fsync();
+  }
+  static constexpr int kXw = 272;  // sh_red[kXw .. kXw + 16): per-warp totals / maxima of the exchanged values
+
+  // after exchange_wait<2>: the maximum of the exchanged values
+  __device__ double fused_max() {
+    if (p.G == 1 || p.G > BLOCK) return xchg_max();
+    const int nw = (p.G + 31) >> 5;
+    double m = -INFINITY;
+    for (int w = 0; w < nw; ++w) m = dmax(m, sh_red[kXw + w]);
+    return m;
+  }
+  // after exchange_wait<1>: exclusive / inclusive prefix of this CTA and the total.  The same expression in every
+  // thread of every CTA (warp offsets summed in warp order + the scanned value), and excl(g) := incl(g - 1).
+  __device__ void fused_prefix(double& excl, double& incl, double& total) {
+    if (p.G == 1 || p.G > BLOCK) { xchg_prefix(excl, incl, total); return; }
+    const int nw = (p.G + 31) >> 5, wc = g >> 5, wp = (g - 1) >> 5;
+    double acc = 0.0, offc = 0.0, offp = 0.0;
+    for (int w = 0; w < nw; ++w) {
+      if (w == wc) offc = acc;
+      if (w == wp) offp = acc;
+      acc += sh_red[kXw + w];
+    }
+    total = acc;
+    incl = offc + sh_x[g];
+    excl = g > 0 ? offp + sh_x[g - 1] : 0.0;
   }
 
   // one thread spins until *cnt >= target (wrap-safe); SCOPE 0: CTA flag in shared memory, 1: GPU,
@@ -534,6 +578,15 @@ struct PfKernel {
     return s < 0 ? s + R : s;
   }
 
+  // l[K] = weight of item K of a gather pass (row element base[K * ST]), 0 beyond the round
+  template <int K>
+  __device__ __forceinline__ void load_weights(const Real* base, int jl0, int len, Real (&l)[kGather], uint64_t once) const {
+    if constexpr (K < kGather) {
+      l[K] = (jl0 + K * kSmootherThreads < len) ? ld_hint_off<K * kSmootherThreads * (int)sizeof(Real)>(base, once) : (Real)0;
+      load_weights<K + 1>(base, jl0, len, l, once);
+    }
+  }
+
   // lineages [c0, c0 + len) of generation tau (ancestor-ring slot `slot_a`) walked back `nlev`
   // generations to smoothing time i (state-ring slot `si`); len <= kChase * kSmootherThreads
   template <bool DIST>
@@ -546,10 +599,10 @@ struct PfKernel {
     const uint64_t keep = p.pol_keep, once = p.pol_once;
     const int kmax = (len + ST - 1) / ST;  // block-uniform number of live items
     int cur[kChase], nxt[kChase];
+    const int first = c0 + st, last = c0 + len - 1;  // idle items re-walk the last lineage of the round
 #pragma unroll
     for (int k = 0; k < kChase; ++k) {
-      const int jl = k * ST + st;
-      cur[k] = (jl < len) ? c0 + jl : c0;
+      cur[k] = min(first + k * ST, last);
       nxt[k] = cur[k];
     }
     // nlev - 1 hops to the ancestors at time i+1, then one more to time i
@@ -600,12 +653,8 @@ struct PfKernel {
     for (int h = 0; h < kChase / kGather; ++h) {
       if (h * kHalf >= kmax) break;
       Real l[kHalf], xc[kHalf], xnext[kHalf];
-#pragma unroll
-      for (int k = 0; k < kHalf; ++k) {
-        const int kk = h * kHalf + k;
-        const int jl = kk * ST + st;
-        l[k] = (jl < len) ? ld_hint(sw_row + (unsigned)(c0 + jl), once) : (Real)0;  // stored shifted weight
-      }
+      // stored shifted weights: one base pointer per pass, the items at immediate offsets
+      load_weights<0>(opaque(sw_row + (unsigned)(first + h * kHalf * ST)), h * kHalf * ST + st, len, l, once);
       gather_states<DIST, kHalf>(xi, xn, si, sn, cur + h * kHalf, nxt + h * kHalf, xc, xnext, once);
 #pragma unroll
       for (int k = 0; k < kHalf; ++k) {
@@ -778,8 +827,7 @@ struct PfKernel {
                                  double u, unsigned long long eval_id, double y_prop, double y_obs,
                                  int c0, int len, int n_lo, int n_hi, bool remote, int owner, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
-    int top = 1;
-    while (top * 2 <= len) top *= 2;
+    const int top = 1 << (31 - __clz(max(len, 1)));  // largest power of two <= len
     const uint32_t ta = smem_base(tile) - 8u;  // address of tile[-1]
     const uint64_t keep = p.pol_keep;
     unsigned short* anc_sh = sh_anc + (size_t)sa * p.anc_stride;  // generation-t row (anc_smem mode)
@@ -822,17 +870,19 @@ struct PfKernel {
         // one descent for the first child of the quad; the first child of the next quad (lane + 1)
         // closes the window in which the three inner children are searched (never a second full
         // descent)
-        const double pa = (nb < p.N) ? position(nb, u, t, inj_u_t, eval_id) : INFINITY;
+        // production flavour: positions beyond N need no guard (they only exceed every CDF entry that
+        // matters; such children are never stored) -- the general flavour may read per-child uniforms
+        const double pa = (!GENERAL || nb < p.N) ? position(nb, u, t, inj_u_t, eval_id) : INFINITY;
         double pin[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e)
-          pin[e] = (nb + 1 + e < p.N) ? position(nb + 1 + e, u, t, inj_u_t, eval_id) : INFINITY;
+          pin[e] = (!GENERAL || nb + 1 + e < p.N) ? position(nb + 1 + e, u, t, inj_u_t, eval_id) : INFINITY;
         int la, lb, li[3];
         if (shuffle_map) {
           la = upper_bound_tile(ta, pa, len, top);
           lb = __shfl_down_sync(0xffffffffu, la, 1);  // lane 31 keeps its own value: empty window
         } else {
-          const double pb = (nb + 4 < p.N) ? position(nb + 4, u, t, inj_u_t, eval_id) : INFINITY;
+          const double pb = (!GENERAL || nb + 4 < p.N) ? position(nb + 4, u, t, inj_u_t, eval_id) : INFINITY;
           upper_bound_pair(ta, pa, pb, len, top, la, lb);
         }
         upper_bound_window3(ta, pin, la, lb, li);
@@ -856,6 +906,10 @@ struct PfKernel {
 #pragma unroll
         for (int e = 0; e < 4; ++e) xp[e] = ld_cg(xp_row + (unsigned)j[e]);
       }
+      // fp32: the four children of a full quad leave in ONE 16-byte store per ring row (a pair store writes half
+      // of every 32-byte sector it touches); fp64 keeps pair stores (the filter path has no registers to hold a quad)
+      constexpr bool kQuadStore = sizeof(Real) == 4;
+      Real xq[4], lq[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
         Real z0, z1;
@@ -879,7 +933,10 @@ struct PfKernel {
         if (la == (Real)123456.789) mx = 0.0;
         PFB_TICK(14);
 #endif
-        if (full) {
+        if (kQuadStore && full) {
+          mx = dmax(mx, dmax((double)la, (double)lb));
+          xq[2 * h] = xa; xq[2 * h + 1] = xb; lq[2 * h] = la; lq[2 * h + 1] = lb;
+        } else if (full) {
           mx = dmax(mx, dmax((double)la, (double)lb));
           store2(x_new + n, xa, xb);
           store2(lw_new + n, la, lb);
@@ -892,6 +949,17 @@ struct PfKernel {
           if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); if (dist) st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         }
         PFB_TICK(15);
+      }
+      if (kQuadStore && full) {
+        store4(x_new + nb, xq);
+        store4(lw_new + nb, lq);
+        if (p.anc_smem) *reinterpret_cast<ushort4*>(anc_sh + nb) = make_ushort4((unsigned short)(c0 + j[0]), (unsigned short)(c0 + j[1]), (unsigned short)(c0 + j[2]), (unsigned short)(c0 + j[3]));
+        else if (remote) *reinterpret_cast<int4*>(anc_new + nb) = make_int4(c0 + j[0], c0 + j[1], c0 + j[2], c0 + j[3]);
+        else st_hint_int4(anc_new + nb, c0 + j[0], c0 + j[1], c0 + j[2], c0 + j[3], keep);
+        if (dist) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_halo(owner, nb + e, xq[e], c0 + j[e]);
+        }
       }
     }
   }
@@ -929,6 +997,13 @@ struct PfKernel {
   }
   static __device__ __forceinline__ void store2(float* dst, float a, float b) {
     *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+  }
+  static __device__ __forceinline__ void store4(float* dst, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void store4(double* dst, const double (&v)[4]) {  // not used (kQuadStore)
+    *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
   }
   static __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }
 
@@ -1051,16 +1126,19 @@ struct PfKernel {
         if (tid == 0) p.filt_part[((size_t)b * (T + 1) + tau) * p.G_loc + g_loc] = f;
       }
       PFB_TICK(1);
-      exchange_wait(s_target);
+      exchange_wait<1>(s_target);
       PFB_TICK(2);
       // prefix over the group + this CTA's children range, evaluated by every warp on its own
       // (lanes 0 / 1 take the two boundaries side by side): no block barrier on the critical path
       double Pg, Pg1, S;
-      xchg_prefix(Pg, Pg1, S);
+      fused_prefix(Pg, Pg1, S);
       const double invS = 1.0 / S;  // the CDF is (prefix sum) * (1/S) everywhere
       int n_begin = 0, n_end = 0;
       const bool pull = GENERAL && p.resampling == 2;  // multinomial: children pull from the global CDF
-      if (!final_step && !pull) {
+      // resident tile: the LAST warp finds the children range while the others normalise the tile (the range is
+      // only needed behind the barrier that ends the normalisation)
+      const bool side_bounds = resident && !final_step && !pull;
+      if (!final_step && !pull && !side_bounds) {
         int nb = 0;
         if (lane < 2) {  // the SAME code on both boundaries: two divergent copies would run one after the other
           const bool fixed = lane == 0 ? (g == 0) : last_cta;
@@ -1084,18 +1162,28 @@ struct PfKernel {
       int traj_cnt = 0;
       if (resident) {
         // normalise the whole tile: (group prefix + sub-chunk carry + local prefix) * (1/S)
-        double base = Pg;
-        for (int c = 0; c < n_chunks; ++c) {
-          double* tile = sh_s + c * kChunk;
-          const int len = min(kChunk, own - c * kChunk);
-#pragma unroll
-          for (int k = 0; k < ITEMS; ++k) {
-            const int jl = k * BLOCK + tid;
-            if (jl < len) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
+        if (side_bounds && warp == kWarps - 1) {
+          if (lane < 2) {  // the SAME code on both boundaries: two divergent copies would run one after the other
+            const bool fixed = lane == 0 ? (g == 0) : last_cta;
+            const int r = lower_bound_child(__dmul_rn(lane == 0 ? Pg : Pg1, invS), u, t, inj_u_t, eval_id);
+            reinterpret_cast<int*>(sh_flags)[2 + lane] = fixed ? (lane == 0 ? 0 : N) : r;
           }
-          base += sh_red[264 + c];
+        } else {
+          const int stride = side_bounds ? BLOCK - 32 : BLOCK;
+          double base = Pg;
+          for (int c = 0; c < n_chunks; ++c) {
+            double* tile = sh_s + c * kChunk;
+            const int len = min(kChunk, own - c * kChunk);
+#pragma unroll 4
+            for (int jl = tid; jl < len; jl += stride) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
+            base += sh_red[264 + c];
+          }
         }
         fsync();
+        if (side_bounds) {
+          n_begin = reinterpret_cast<const int*>(sh_flags)[2];
+          n_end = reinterpret_cast<const int*>(sh_flags)[3];
+        }
         if (final_step) {
           // trajectory draw (standard.py:104): k = #{ j : cdf[j] <= u_final }
           for (int jl = tid; jl < own; jl += BLOCK)
@@ -1183,9 +1271,9 @@ struct PfKernel {
         PFB_TICK(5);
         exchange_arrive(mx);
         PFB_TICK(10);
-        exchange_wait();
+        exchange_wait<2>();
         PFB_TICK(6);
-        m = xchg_max();
+        m = fused_max();
         PFB_TICK(7);
       }
     }

@@ -42,7 +42,7 @@ for _ in range(a.reps):
     ms.append(eng.last_kernel_ms())
 ll = eng.fetch_log_like()
 units = a.B * a.N * a.T
-print("N=%d T=%d B=%d %s G=%d groups=%d: kernel ms %s -> %.2f G particle-steps/s, %.2f us/time-step, ll[0]=%.4f"
+print("N=%d T=%d B=%d %s G=%d groups=%d: kernel ms %s -> %.2f G particle-steps/s, %.2f us/time-step, ll[0]=%.12f"
       % (a.N, a.T, a.B, a.dtype, eng.info("ctas_per_filter"), eng.info("n_groups"),
          ["%.3f" % m for m in ms], units / min(ms) / 1e6, min(ms) * 1e3 / a.T, ll[0]))
 prof = eng.debug_profile()
