@@ -223,7 +223,9 @@ __device__ __forceinline__ void normal_pair_from_bits(const uint32_t (&r)[4], fl
   const float u2 = (float)(r[2] >> 8) * (1.0f / 16777216.0f);
   const float rad = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  // angle 2 pi u2 - pi in [-pi, pi): the range in which the fast sine / cosine keep their 2^-21 absolute error
+  // (the same order as __logf above; any uniform angle serves Box-Muller)
+  __sincosf(fmaf(u2, 6.28318530717958648f, -3.14159265358979324f), &s, &c);
   z_even = rad * c;
   z_odd = rad * s;
 }

@@ -827,6 +827,7 @@ struct PfKernel {
                                  double u, unsigned long long eval_id, double y_prop, double y_obs,
                                  int c0, int len, int n_lo, int n_hi, bool remote, int owner, double& mx) {
     const int q0 = n_lo >> 2, q1 = (n_hi + 3) >> 2;
+    Real mxr = (Real)(-INFINITY);  // running maximum in the storage type (fp32: one FMNMX, no conversions)
     const int top = 1 << (31 - __clz(max(len, 1)));  // largest power of two <= len
     const uint32_t ta = smem_base(tile) - 8u;  // address of tile[-1]
     const uint64_t keep = p.pol_keep;
@@ -908,7 +909,7 @@ struct PfKernel {
       }
       // fp32: the four children of a full quad leave in ONE 16-byte store per ring row (a pair store writes half
       // of every 32-byte sector it touches); fp64 keeps pair stores (the filter path has no registers to hold a quad)
-      constexpr bool kQuadStore = sizeof(Real) == 4;
+      constexpr bool kQuadStore = sizeof(Real) == 4;  // (kept per quad-loop iteration)
       Real xq[4], lq[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
@@ -934,10 +935,10 @@ struct PfKernel {
         PFB_TICK(14);
 #endif
         if (kQuadStore && full) {
-          mx = dmax(mx, dmax((double)la, (double)lb));
+          mxr = rmax(mxr, rmax(la, lb));
           xq[2 * h] = xa; xq[2 * h + 1] = xb; lq[2 * h] = la; lq[2 * h + 1] = lb;
         } else if (full) {
-          mx = dmax(mx, dmax((double)la, (double)lb));
+          mxr = rmax(mxr, rmax(la, lb));
           store2(x_new + n, xa, xb);
           store2(lw_new + n, la, lb);
           if (p.anc_smem) *reinterpret_cast<ushort2*>(anc_sh + n) = make_ushort2((unsigned short)(c0 + j[2 * h]), (unsigned short)(c0 + j[2 * h + 1]));
@@ -945,8 +946,8 @@ struct PfKernel {
           else st_hint_int2(anc_new + n, c0 + j[2 * h], c0 + j[2 * h + 1], keep);
           if (dist) { st_halo(owner, n, xa, c0 + j[2 * h]); st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         } else {
-          if (n >= n_lo && n < n_hi) { mx = dmax(mx, (double)la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); if (dist) st_halo(owner, n, xa, c0 + j[2 * h]); }
-          if (n + 1 >= n_lo && n + 1 < n_hi) { mx = dmax(mx, (double)lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); if (dist) st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
+          if (n >= n_lo && n < n_hi) { mxr = rmax(mxr, la); x_new[n] = xa; lw_new[n] = la; if (p.anc_smem) anc_sh[n] = (unsigned short)(c0 + j[2 * h]); else if (remote) anc_new[n] = c0 + j[2 * h]; else st_hint_int(anc_new + n, c0 + j[2 * h], keep); if (dist) st_halo(owner, n, xa, c0 + j[2 * h]); }
+          if (n + 1 >= n_lo && n + 1 < n_hi) { mxr = rmax(mxr, lb); x_new[n + 1] = xb; lw_new[n + 1] = lb; if (p.anc_smem) anc_sh[n + 1] = (unsigned short)(c0 + j[2 * h + 1]); else if (remote) anc_new[n + 1] = c0 + j[2 * h + 1]; else st_hint_int(anc_new + n + 1, c0 + j[2 * h + 1], keep); if (dist) st_halo(owner, n + 1, xb, c0 + j[2 * h + 1]); }
         }
         PFB_TICK(15);
       }
@@ -962,6 +963,7 @@ struct PfKernel {
         }
       }
     }
+    mx = dmax(mx, (double)mxr);
   }
 
   // children [n_lo, n_hi) of the tile, written to the rank that owns their index range (own rings,
@@ -1006,6 +1008,9 @@ struct PfKernel {
     *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
   }
   static __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }
+  // maximum that skips a NaN second argument, in the storage type
+  static __device__ __forceinline__ double rmax(double a, double b) { return (b > a) ? b : a; }
+  static __device__ __forceinline__ float rmax(float a, float b) { return (b > a) ? b : a; }
 
   // ---- one filter evaluation (all T steps) -------------------------------------------------
   __device__ void run_filter(int b, int b_idx) {
@@ -1169,13 +1174,24 @@ struct PfKernel {
             reinterpret_cast<int*>(sh_flags)[2 + lane] = fixed ? (lane == 0 ? 0 : N) : r;
           }
         } else {
-          const int stride = side_bounds ? BLOCK - 32 : BLOCK;
           double base = Pg;
           for (int c = 0; c < n_chunks; ++c) {
             double* tile = sh_s + c * kChunk;
             const int len = min(kChunk, own - c * kChunk);
-#pragma unroll 4
-            for (int jl = tid; jl < len; jl += stride) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
+            if (side_bounds) {  // BLOCK - 32 threads cover the sub-chunk (compile-time strides: immediate offsets)
+              constexpr int kStride = BLOCK - 32, kIter = (kChunk + kStride - 1) / kStride;
+#pragma unroll
+              for (int k = 0; k < kIter; ++k) {
+                const int jl = k * kStride + tid;
+                if (jl < len) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < ITEMS; ++k) {
+                const int jl = k * BLOCK + tid;
+                if (jl < len) tile[jl] = __dmul_rn(__dadd_rn(base, tile[jl]), invS);
+              }
+            }
             base += sh_red[264 + c];
           }
         }
