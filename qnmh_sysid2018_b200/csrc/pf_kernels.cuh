@@ -195,7 +195,7 @@ struct PfKernel {
   // `s_target` > 0: additionally wait until the smoother warps of every CTA of the group have
   // completed their first s_target jobs (their reads of the ring slots the next phase overwrites).
   // MODE 0: sh_x[0..G) = the exchanged values (xchg_max / xchg_prefix reduce them in every warp).  MODE 1 / 2
-  // (groups of up to BLOCK CTAs): the warps that fetch the values scan / maximise their 32 in registers, so that
+  // (groups of up to kXmax CTAs): the warps that fetch the values scan / maximise their 32 in registers, so that
   // after ONE more barrier a thread needs a handful of broadcast loads -- see fused_prefix / fused_max.
   template <int MODE = 0>
   __device__ void exchange_wait(unsigned s_target = 0) {
@@ -216,17 +216,17 @@ struct PfKernel {
         ab = dist ? wait_counter<2>(cnt + 16, s_target * (unsigned)G) : wait_counter<1>(cnt + 16, s_target * (unsigned)G);
     }
     aborted = fsync_or(ab);  // block-uniform; orders the reads below after the acquire
-    if (MODE != 0 && G <= BLOCK) {
-      if (tid < ((G + 31) & ~31)) {  // whole warps
+    if (MODE != 0 && G <= kXmax) {
+      for (int i = tid; i < ((G + 31) & ~31); i += BLOCK) {  // whole warps: segment i / 32 of the values
         if (MODE == 1) {
-          const double incl = warp_inclusive_scan(tid < G ? ld_cg(val + tid) : 0.0, lane);
-          sh_x[tid < G ? tid : G - 1] = incl;  // (idle lanes of the last warp repeat its total)
-          if (lane == 31) sh_red[kXw + warp] = incl;
+          const double incl = warp_inclusive_scan(i < G ? ld_cg(val + i) : 0.0, lane);
+          sh_x[i < G ? i : G - 1] = incl;  // (idle lanes of the last segment repeat its total)
+          if (lane == 31) sh_red[kXw + (i >> 5)] = incl;
         } else {
-          double v = tid < G ? ld_cg(val + tid) : -INFINITY;
+          double v = i < G ? ld_cg(val + i) : -INFINITY;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-          if (lane == 0) sh_red[kXw + warp] = v;
+          if (lane == 0) sh_red[kXw + (i >> 5)] = v;
         }
       }
     } else {
@@ -234,11 +234,12 @@ struct PfKernel {
     }
     fsync();
   }
-  static constexpr int kXw = 272;  // sh_red[kXw .. kXw + 16): per-warp totals / maxima of the exchanged values
+  static constexpr int kXw = 272;    // sh_red[kXw .. kXw + 32): per-segment totals / maxima of the exchanged values
+  static constexpr int kXmax = 1024;  // largest group the fused reductions serve (8 GPUs x 128 CTAs)
 
   // after exchange_wait<2>: the maximum of the exchanged values
   __device__ double fused_max() {
-    if (p.G == 1 || p.G > BLOCK) return xchg_max();
+    if (p.G == 1 || p.G > kXmax) return xchg_max();
     const int nw = (p.G + 31) >> 5;
     double m = -INFINITY;
     for (int w = 0; w < nw; ++w) m = dmax(m, sh_red[kXw + w]);
@@ -247,7 +248,7 @@ struct PfKernel {
   // after exchange_wait<1>: exclusive / inclusive prefix of this CTA and the total.  The same expression in every
   // thread of every CTA (warp offsets summed in warp order + the scanned value), and excl(g) := incl(g - 1).
   __device__ void fused_prefix(double& excl, double& incl, double& total) {
-    if (p.G == 1 || p.G > BLOCK) { xchg_prefix(excl, incl, total); return; }
+    if (p.G == 1 || p.G > kXmax) { xchg_prefix(excl, incl, total); return; }
     const int nw = (p.G + 31) >> 5, wc = g >> 5, wp = (g - 1) >> 5;
     double acc = 0.0, offc = 0.0, offp = 0.0;
     for (int w = 0; w < nw; ++w) {
@@ -1304,7 +1305,7 @@ template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB, bool GENERAL
 __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_kernel(const DeviceProblem prob) {
   static_assert(BLOCK == 512 && PFB_SMOOTH_THREADS == 128, "the setmaxnreg split below assumes 512 + 128 threads");
   extern __shared__ double pf_smem[];
-  __shared__ double sh_red[9 * 32 + 8];
+  __shared__ double sh_red[9 * 32 + 8 + 8];  // [0, 264): block reductions, [264, 272): sub-chunk totals, [272, 304): exchange segments
   __shared__ double sh_c[kNumConsts];
   __shared__ double sh_sred[(PFB_SMOOTH_THREADS / 32) * (kMaxParams + 1)];
   __shared__ unsigned sh_flags[4];
