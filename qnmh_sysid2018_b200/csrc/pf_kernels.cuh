@@ -83,7 +83,7 @@ struct DeviceProblem {
   int anc_smem;    // one CTA per filter and N <= 65535: the ancestor ring lives in shared memory as
   int anc_stride;  //   uint16 [RA][anc_stride] (lineage walks at shared-memory latency, no global traffic)
   double* xval;    // [n_groups][2][G]
-  unsigned* xcount;  // [n_groups] arrival counters (padded to 32 words each)
+  unsigned* xcount;  // [n_groups] arrival counters (padded to 32 words each; a distributed filter: 2080 words)
   int* abort_flag;
   double* stat_m;     // [B][T+1]
   double* stat_S;     // [B][T+1]
@@ -182,7 +182,7 @@ struct PfKernel {
       // every rank's counter at system scope (NVLink peer stores); thread r serves rank r
       if (tid < p.R) {
         p.peer_xval[tid][(size_t)(epoch & 1u) * G + g] = v;
-        red_release_sys_add_u32(p.peer_xcount[tid], 1u);
+        red_release_sys_add_u32(p.peer_xcount[tid] + kDistX + kDistLine * dist_slot(), 1u);
       }
     } else if (tid == 0) {
       p.xval[((size_t)q * 2 + (epoch & 1u)) * G + g] = v;
@@ -210,10 +210,17 @@ struct PfKernel {
     const double* val = p.xval + ((size_t)q * 2 + (epoch & 1u)) * G;
     const unsigned* cnt = p.xcount + (size_t)q * 32;
     int ab = 0;
-    if (tid == 0) {
-      ab = dist ? wait_counter<2>(cnt, epoch * (unsigned)G) : wait_counter<1>(cnt, epoch * (unsigned)G);
-      if (!ab && s_target != 0)
-        ab = dist ? wait_counter<2>(cnt + 16, s_target * (unsigned)G) : wait_counter<1>(cnt + 16, s_target * (unsigned)G);
+    if (dist) {
+      // R * kDistSpread counters per rank (dist_slot): one polling lane each, so that the R * G_loc remote
+      // increments of an exchange do not queue up on ONE address
+      if (tid < p.R * kDistSpread) {
+        const unsigned per = (unsigned)dist_slot_arrivals(tid % kDistSpread);
+        ab = wait_counter<2>(cnt + kDistX + kDistLine * tid, epoch * per);
+        if (!ab && s_target != 0) ab = wait_counter<2>(cnt + kDistS + kDistLine * tid, s_target * per);
+      }
+    } else if (tid == 0) {
+      ab = wait_counter<1>(cnt, epoch * (unsigned)G);
+      if (!ab && s_target != 0) ab = wait_counter<1>(cnt + 16, s_target * (unsigned)G);
     }
     aborted = fsync_or(ab);  // block-uniform; orders the reads below after the acquire
     if (MODE != 0 && G <= kXmax) {
@@ -234,8 +241,8 @@ struct PfKernel {
     }
     fsync();
   }
-  static constexpr int kXw = 272;    // sh_red[kXw .. kXw + 32): per-segment totals / maxima of the exchanged values
-  static constexpr int kXmax = 1024;  // largest group the fused reductions serve (8 GPUs x 128 CTAs)
+  static constexpr int kXw = 272;    // sh_red[kXw .. kXw + 37): per-segment totals / maxima of the exchanged values
+  static constexpr int kXmax = 1184;  // largest group the fused reductions serve (8 GPUs x 148 CTAs)
 
   // after exchange_wait<2>: the maximum of the exchanged values
   __device__ double fused_max() {
@@ -260,6 +267,18 @@ struct PfKernel {
     incl = offc + sh_x[g];
     excl = g > 0 ? offp + sh_x[g - 1] : 0.0;
   }
+
+  // Distributed filter: the arrival / smoother-progress counters of a rank are spread over R * kDistSpread slots
+  // (source rank x g_loc mod kDistSpread), one 128-byte line each, behind the single-GPU words: slot s of the
+  // exchange arrivals at word kDistX + 32 s, of the smoother jobs at kDistS + 32 s.  Counter words per group:
+  // kDistS + 1024 (pfb200.cu: counter_bytes allocates and clears them).
+#ifndef PFB_DIST_SPREAD
+#define PFB_DIST_SPREAD 4
+#endif
+  static constexpr int kDistSpread = PFB_DIST_SPREAD, kDistLine = 32, kDistX = 32, kDistS = 32 + 32 * kDistLine;
+  __device__ __forceinline__ int dist_slot() const { return p.rank * kDistSpread + g_loc % kDistSpread; }
+  // CTAs of one rank that arrive on sub-counter s
+  __device__ __forceinline__ int dist_slot_arrivals(int s) const { return (p.G_loc - s + kDistSpread - 1) / kDistSpread; }
 
   // one thread spins until *cnt >= target (wrap-safe); SCOPE 0: CTA flag in shared memory, 1: GPU,
   // 2: system (peer GPUs).  Returns 1 when the wait was abandoned (spin limit / abort flag).
@@ -297,7 +316,7 @@ struct PfKernel {
     if (p.G == 1) {
       if (st == 0) st_release_cta_shared_u32(sh_flags + 1, sjobs);
     } else if (dist) {
-      if (st < p.R) red_release_sys_add_u32(p.peer_xcount[st] + 16, 1u);
+      if (st < p.R) red_release_sys_add_u32(p.peer_xcount[st] + kDistS + kDistLine * dist_slot(), 1u);
     } else if (st == 0) {
       red_release_add_u32(p.xcount + (size_t)q * 32 + 16, 1u);
     }
@@ -1305,7 +1324,7 @@ template <int MODEL, typename Real, int BLOCK, int ITEMS, int MINB, bool GENERAL
 __global__ void __launch_bounds__(BLOCK + PFB_SMOOTH_THREADS, 1) pf_persistent_kernel(const DeviceProblem prob) {
   static_assert(BLOCK == 512 && PFB_SMOOTH_THREADS == 128, "the setmaxnreg split below assumes 512 + 128 threads");
   extern __shared__ double pf_smem[];
-  __shared__ double sh_red[9 * 32 + 8 + 8];  // [0, 264): block reductions, [264, 272): sub-chunk totals, [272, 304): exchange segments
+  __shared__ double sh_red[9 * 32 + 8 + 40];  // [0, 264): block reductions, [264, 272): sub-chunk totals, [272, 309): exchange segments
   __shared__ double sh_c[kNumConsts];
   __shared__ double sh_sred[(PFB_SMOOTH_THREADS / 32) * (kMaxParams + 1)];
   __shared__ unsigned sh_flags[4];

@@ -59,6 +59,10 @@ int fail(int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
 
+// arrival counters: 32 words per group; a distributed filter (one group) spreads its system-scope counters over
+// 2 x 32 slots of one 128-byte line each behind them (pf_kernels.cuh: kDistX / kDistS)
+static size_t counter_bytes(int n_groups) { return (size_t)(n_groups * 32 > 2080 ? n_groups * 32 : 2080) * 4; }
+
 struct DevBuf {
   void* ptr = nullptr;
   size_t cap = 0;
@@ -454,7 +458,10 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
       else if (B == 1) G_loc = ((N + R - 1) / R + kBlock - 1) / kBlock;
       else G_loc = (N <= 4 * kChunk) ? 1 : (N + kChunk - 1) / kChunk;
       if (G_loc > capacity) G_loc = capacity;
-      if (G_loc * R > 1024) G_loc = 1024 / R;
+      {  // group size limit (exchange staging, fused reductions): 1184 = 8 GPUs x 148 CTAs
+        const int g_max = 1184;
+        if (G_loc * R > g_max) G_loc = g_max / R;
+      }
       if (G_loc < 1) G_loc = 1;
       G = G_loc * R;
       per = (N + G - 1) / G;
@@ -630,7 +637,7 @@ int pfb200_configure(pfb200_handle* h, int n_filters, int no_particles, int no_o
   if (resampling == PFB200_RESAMPLE_MULTINOMIAL)  // distributed: every rank keeps a copy of the WHOLE CDF
     CUDA_TRY(h->cdf_g.reserve(R > 1 ? ((size_t)N + 32) * 8 : (size_t)h->n_ws * p.NS * 8));
   CUDA_TRY(h->xval.reserve((size_t)n_groups * 2 * G * 8));
-  CUDA_TRY(h->xcount.reserve((size_t)n_groups * 32 * 4));
+  CUDA_TRY(h->xcount.reserve(counter_bytes(n_groups)));
   CUDA_TRY(h->abortf.reserve(16));
   CUDA_TRY(h->stat_m.reserve((size_t)B * T1 * 8));
   CUDA_TRY(h->stat_S.reserve((size_t)B * T1 * 8));
@@ -710,7 +717,7 @@ int pfb200_execute(pfb200_handle* h) {
     p.sjobs0 = h->dist_sjobs;               // smoother jobs per CTA and launch: lag times L..T-1 + the tail
     if (p.do_smoother) h->dist_sjobs += (unsigned)(p.T > p.L ? p.T - p.L : 0) + 1u;
   } else {
-    CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, (size_t)p.n_groups * 32 * 4, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->xcount.ptr, 0, counter_bytes(p.n_groups), h->stream));
   }
   CUDA_TRY(cudaMemsetAsync(h->abortf.ptr, 0, 16, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->traj_k.ptr, 0, (size_t)p.B * 4, h->stream));
@@ -921,7 +928,7 @@ int pfb200_dist_export(pfb200_handle* h, void* out, int bytes) {
   for (int k = 0; k < kDistBufs; ++k)
     if (ptrs[k]) CUDA_TRY(cudaIpcGetMemHandle(&hs[k], ptrs[k]));
   // fresh counters; the caller synchronises all ranks (host barrier) between connect and execute
-  CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
+  CUDA_TRY(cudaMemset(h->xcount.ptr, 0, counter_bytes(h->prob.n_groups)));
   h->dist_epoch = 0;
   h->dist_sjobs = 0;
   return PFB200_OK;
@@ -982,12 +989,25 @@ int pfb200_dist_connect_local(pfb200_handle* const* handles, int world) {
       p.peer_x[q] = o->x_ring.ptr; p.peer_lw[q] = o->logw.ptr; p.peer_anc[q] = o->anc.as<int>();
       p.peer_xval[q] = o->xval.as<double>(); p.peer_xcount[q] = o->xcount.as<unsigned>(); p.peer_cdf[q] = o->cdf_g.as<double>();
     }
-    CUDA_TRY(cudaMemset(h->xcount.ptr, 0, (size_t)h->prob.n_groups * 32 * 4));
+    CUDA_TRY(cudaMemset(h->xcount.ptr, 0, counter_bytes(h->prob.n_groups)));
     h->dist_epoch = 0;
     h->dist_sjobs = 0;
   }
   for (int r = 0; r < world; ++r) {
     CUDA_TRY(cudaSetDevice(handles[r]->device));
+    if (same_device) {
+      // Ranks on ONE device are kernels that wait for each other, launched one after the other by this thread:
+      // nothing pfb200_execute enqueues behind the first rank's kernel may still have to be LOADED (CUDA loads
+      // kernels lazily at their first launch, and that load can wait for the running -- spinning -- kernel, so
+      // the second rank would never be launched).  Touch everything execute uses before the first launch.
+      cudaFuncAttributes fa;
+      CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)handles[r]->kernel));
+      CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)pf_finalize_kernel));
+      CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)pf_loglike_kernel));
+      CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)pf_trajectory_kernel<double>));
+      CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)pf_trajectory_kernel<float>));
+      CUDA_TRY(cudaMemsetAsync(handles[r]->abortf.ptr, 0, 16, handles[r]->stream));
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     handles[r]->dist_connected = true;
     handles[r]->dist_same_device = same_device;

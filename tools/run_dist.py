@@ -19,6 +19,7 @@ ap.add_argument("--L", type=int, default=10)
 ap.add_argument("--dtype", default="float64")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-smoother", action="store_true")
+ap.add_argument("--ctas", type=int, default=0, help="CTAs per rank (0: automatic)")
 ap.add_argument("--general", action="store_true", help="single GPU: general kernel flavour (stratified resampling)")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -30,7 +31,7 @@ obs = bench.synthetic_obs("lgss", a.T)
 for k in a.log2:
     N = 1 << k
     if world > 1:
-        dpf = DistributedParticleFilter("lgss", a.dtype, local)
+        dpf = DistributedParticleFilter("lgss", a.dtype, local, ctas_per_rank=a.ctas)
         dpf.prepare(obs, bench.THETA_LGSS, N, a.L, not a.no_smoother, seed=1)
         eng = dpf.engine
     else:
@@ -53,6 +54,14 @@ for k in a.log2:
         print("C5 N=2^%d T=%d %s on %d GPU(s): %.3f ms -> %.2f G particle-steps/s (%.1f us/step), ctas/rank %d, tile_cap %d, ll %.4f"
               % (k, a.T, a.dtype, world, float(t[0]), N * a.T / float(t[0]) / 1e6, float(t[0]) * 1e3 / a.T,
                  eng.info("ctas_per_rank"), eng.info("tile_cap"), ll), flush=True)
+    prof = eng.debug_profile()
+    if rank == 0 and prof.any():  # -DPFB_PROFILE builds: per-phase clocks of this rank's CTAs (thread 0 of each)
+        names = ["A:scan(+rest)", "filt block_sum", "exchange1 wait", "prefix+bounds", "children", "block_max", "exchange2 wait",
+                 "xchg_max", "A:load+exp", "X1 arrive", "X2 arrive", "B: search", "-", "B: gather + normals", "B: propagate/weight", "B: stores"]
+        per_step = prof / float(a.T) / 1.965e3
+        for i, nm in enumerate(names):
+            print("   %-20s mean %7.2f us  max %7.2f us  min %7.2f us" % (nm, per_step[:, i].mean(), per_step[:, i].max(), per_step[:, i].min()), flush=True)
+        print("   total (mean over CTAs) %.2f us/step" % per_step[:, :13].sum(axis=1).mean(), flush=True)
     del eng
     if world > 1:
         del dpf
