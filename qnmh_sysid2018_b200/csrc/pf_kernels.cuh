@@ -1231,8 +1231,14 @@ struct PfKernel {
             for (int jl = tid; jl < own; jl += BLOCK) cg[j_begin + jl] = sh_s[jl];
           }
         } else {
-          children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id,
-                       y_prop, y_obs, j_begin, own, n_begin, n_end, mx);
+          // Degenerate generation (every weight NaN: all log-weights -inf or NaN -- a derailed proposal): no
+          // position is below any CDF entry, the reference's search leaves EVERY ancestor at particle 0
+          // (resampling.pyx:78-83) and the log-likelihood is NaN from here on.  The children ranges above would
+          // hand all N children to CTA 0 (11x the step time at C4's shape); every CTA takes the children of its
+          // own index range instead, from a one-entry "tile" at particle 0 -- same ancestors, same states.
+          const bool degen = S != S && !dist;
+          children_all(sh_s, x_prev, x_new, lw_new, anc_new, inj_z_t, inj_u_t, t, u, eval_id, y_prop, y_obs,
+                       degen ? 0 : j_begin, degen ? 1 : own, degen ? j_begin : n_begin, degen ? j_end : n_end, mx);
         }
       } else {
         int n_cursor = n_begin;

@@ -336,3 +336,52 @@ def test_sharded_filter_two_ranks_on_one_gpu(N, T, L, gl, resampling):
     assert d2["log_like_per_rank"][0] == one2["log_like"][0]
     np.testing.assert_allclose(d2["grad_terms"][0], one2["grad_terms"][0], rtol=1e-10, atol=1e-11)
     sh.close()
+
+
+# ---------------------------------------------------------------------------------------------- (i)
+@pytest.mark.parametrize("N,G", [(6000, 12), (4096, 1)])
+def test_degenerate_generation_matches_oracle(N, G):
+    """An observation that sends every log-weight to -inf (a derailed MH proposal does the same): all weights
+    of that generation are NaN, the reference's search leaves every ancestor at particle 0
+    (resampling.pyx:78-83) and the log-likelihood is NaN; the particles stay finite.  Device = oracle."""
+    import warnings
+    T, L = 12, 3
+    obs = _obs("lgss", T, 8)
+    obs[5] = 1e200
+    draws = orc.random_draws(np.random.default_rng(N), N, T)
+    eng = _engine("lgss", ctas_per_filter=G, cluster=-1)
+    eng.configure(obs, THETA["lgss"], N, L, True, True, 0.0, "systematic", draws=draws, store_history=True)
+    eng.execute()
+    hist, out = _first(eng.fetch_history()), eng.fetch()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = orc.smoother(orc.MODEL_LGSS, THETA["lgss"], obs, N, L, draws)
+    assert eng.info("ctas_per_filter") == G
+    assert np.isnan(out["log_like"][0]) and np.isnan(ref["log_like"])
+    assert np.all(ref["ancestors"][6] == 0)
+    np.testing.assert_array_equal(hist["ancestors"][1:], ref["ancestors"][1:])
+    np.testing.assert_array_equal(hist["particles"], ref["particles"])
+    assert np.all(np.isfinite(hist["particles"]))
+
+
+def test_degenerate_generations_do_not_serialise_the_step():
+    """With NaN weights the children ranges used to hand all N children to CTA 0 (11x the step time at C4's
+    shape); every CTA now takes its own index range."""
+    N, T, L = 1 << 16, 60, 10
+    obs = _obs("sv", T, 3)
+    ms = {}
+    for name, bad in (("regular", False), ("derailed", True)):
+        o = obs.copy()
+        if bad:
+            o[3::4] = 1e200  # every 4th generation degenerates
+        eng = _engine("sv", cluster=-1)
+        eng.configure(o, THETA["sv"], N, L, True, True, 0.0, "systematic", seed=5)
+        for _ in range(3):
+            eng.execute()
+            eng.synchronize()
+        ms[name] = eng.last_kernel_ms()
+        assert eng.info("ctas_per_filter") >= 64
+        ll = eng.fetch_log_like()[0]
+        assert np.isnan(ll) == bad
+    print("kernel ms: %s" % ms)
+    assert ms["derailed"] < 2.5 * ms["regular"], ms
