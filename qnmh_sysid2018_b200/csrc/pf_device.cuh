@@ -312,9 +312,11 @@ struct ModelOps<MODEL, double> {
       const double zz = __ddiv_rn(__dsub_rn(y, pred), c[C_SVRHO]);
       return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), c[C_RHOTERM]);
     } else {
-      const double vol = exp(__dmul_rn(0.5, x));
-      const double zz = __ddiv_rn(y, vol);
-      return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), log(vol));
+      // norm.logpdf(y, 0, exp(x / 2)) with 1 / vol = exp(-x / 2) and log(vol) = x / 2: ONE exp instead of
+      // exp -> division -> log (a dependent chain of ~150 instructions on the filter warps' critical path; 10 % of
+      // the step at C4's shape).  Differs from the reference's expression by a few ulp of the terms (tests: 1e-13).
+      const double zz = __dmul_rn(y, exp(__dmul_rn(-0.5, x)));
+      return __dsub_rn(__dsub_rn(__dmul_rn(-__dmul_rn(zz, zz), 0.5), PFB_NORM_LOGC), __dmul_rn(0.5, x));
     }
   }
   // log_joint_gradient(next_state, cur_state, time_index); out[p] in parameter order
