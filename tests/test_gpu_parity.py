@@ -362,6 +362,26 @@ def test_filtered_means_and_loglik_against_exact_kalman():
         assert np.all(np.isfinite(s32)) and np.abs(s32 - s64).max() < 1.5, (s32, s64)
 
 
+def test_score_and_smoothed_means_against_kalman_rts():
+    """Statistical check of the fixed-lag smoother against the exact answers: the Kalman RTS
+    smoother's means and its exact score terms (oracle/kalman_oracle.py, pinned to the reference's
+    kalman_methods/standard.py:86-178).  The reference stores the term of the pair (x_{i-1}, x_i) at index i, the
+    particle smoother the pair (x_i, x_{i+1}) at index i; the first / last terms (the reference's smo[0] = 0
+    convention, the tail of the fixed lag) are left out.  Tolerances: Monte Carlo error at N = 2^18 plus the
+    fixed-lag bias (phi^L), calibrated with the NumPy oracle at N = 40 000 (0.07 per term, 0.06 on the sums)."""
+    from oracle import kalman_oracle as ko
+    theta, T, N, L = np.array([0.2, 0.5, 1.0, 0.5]), 120, 1 << 18, 10
+    obs = _synthetic_obs("lgss", theta, T, np.random.default_rng(11))
+    m0, p0 = ko.stationary_prior(theta)
+    ks = ko.kalman_smoother(obs, theta, initial_state=m0, initial_cov=p0)
+    out = _engine("lgss").run(obs, theta, N, L, True, True, 0.0, "systematic", seed=5)
+    pf = out["grad_terms"][0][:3, 2:T - 1]
+    kf = ks["gradient_part"][:3, 3:T]
+    assert np.abs(pf - kf).max() < 0.08, np.abs(pf - kf).max(axis=1)
+    assert np.abs(pf.sum(axis=1) - kf.sum(axis=1)).max() < 0.15, (pf.sum(axis=1), kf.sum(axis=1))
+    assert np.abs(out["smo"][0][2:T - 1] - ks["smo_state_est"][2:T - 1]).max() < 0.03
+
+
 def test_philox_loglik_is_consistent_with_kalman():
     """Statistical check without injected noise: the PF log-likelihood on the reference
     data at N=2^16 is within Monte Carlo error of the reference Kalman log-likelihood."""
