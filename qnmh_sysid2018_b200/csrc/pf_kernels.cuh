@@ -929,7 +929,7 @@ struct PfKernel {
       }
       // fp32: the four children of a full quad leave in ONE 16-byte store per ring row (a pair store writes half
       // of every 32-byte sector it touches); fp64 keeps pair stores (the filter path has no registers to hold a quad)
-      constexpr bool kQuadStore = sizeof(Real) == 4;  // (kept per quad-loop iteration)
+      constexpr bool kQuadStore = sizeof(Real) == 4;
       Real xq[4], lq[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // two Box-Muller pairs
